@@ -1,0 +1,196 @@
+// Batched monotonic alignment search on the device.
+//
+// Replaces the reference's device→host→numba→device round trip
+//   VarianceAdaptor.binarize_attention   fs2/variance_adaptor.py:160-181
+//   mas_width1 / b_mas                   fs2/attn/alignment.py:48-85
+// Result is bit-exact w.r.t. the numba code for the same fp32 log-probabilities: the forward
+// recurrence does the same fp32 add of max(left-up, up); the direction taken by the backtrack
+// (`log_p[i-1,j-1] >= log_p[i-1,j]`, tie → diagonal) is recorded as one bit per cell while the
+// row is live in registers, so the backtrack never re-reads log_p.
+//
+// Layout: one CTA per utterance; thread t owns column(s) t + c·blockDim of the current row
+// (`prev[c]` lives in a register), the left neighbour comes from `__shfl_up` and, across warp
+// and chunk boundaries, from a double-buffered shared-memory word; one `__syncthreads` per mel
+// frame.  Rows are prefetched PF frames ahead in registers.  The backtrack is done by warp 0,
+// 32 frames per step: lane r fetches the two direction words that can hold frame (top−r)'s
+// column, then the dependent chain runs through shuffles only.
+#include "common.cuh"
+
+namespace fs2k {
+
+constexpr int kMasPF = 8;  // mel frames kept in flight per thread
+
+template <int CHUNKS, bool TAKE_LOG>
+__global__ void __launch_bounds__(1024, 1)
+mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs if TAKE_LOG)
+              const int* __restrict__ in_lens,   // [B] text lengths
+              const int* __restrict__ out_lens,  // [B] mel lengths
+              int F, int T, int W,               // W = ceil(T/32) direction words per frame
+              uint32_t* __restrict__ dirs,       // [B,F,W] workspace
+              int* __restrict__ path,            // [B,F] column of frame f, −1 on padding
+              int* __restrict__ durations)       // [B,T]
+{
+    const int b = blockIdx.x;
+    const int n_text = min(in_lens[b], T);
+    const int n_mel = min(out_lens[b], F);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float NEG_INF = -INFINITY;
+    __shared__ float bnd[2][CHUNKS * 32];
+
+    const float* x = attn + (size_t)b * F * T;
+    uint32_t* d = dirs + (size_t)b * F * W;
+    int* p = path + (size_t)b * F;
+    int* dur = durations + (size_t)b * T;
+
+    for (int t = tid; t < T; t += blockDim.x) dur[t] = 0;
+    for (int f = max(n_mel, 0) + tid; f < F; f += blockDim.x) p[f] = -1;
+    if (n_mel <= 0 || n_text <= 0) {
+        for (int f = tid; f < F; f += blockDim.x) p[f] = -1;
+        return;
+    }
+
+    int col[CHUNKS];
+    bool live[CHUNKS];
+    float prev[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        col[c] = c * blockDim.x + tid;
+        live[c] = col[c] < n_text;
+        // row 0: log_p[0,0] = x[0,0]; log_p[0,1:] = -inf        (alignment.py:53-54)
+        float v = NEG_INF;
+        if (col[c] == 0) {
+            v = x[0];
+            if (TAKE_LOG) v = logf(v);
+        }
+        prev[c] = v;
+        if (lane == 31) bnd[0][c * nwarps + warp] = v;
+    }
+    // prefetch ring: xr[u][c] holds row (i0+u)
+    float xr[kMasPF][CHUNKS];
+#pragma unroll
+    for (int u = 0; u < kMasPF; ++u)
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            int r = 1 + u;
+            xr[u][c] = (live[c] && r < n_mel) ? x[(size_t)r * T + col[c]] : 0.f;
+        }
+    __syncthreads();
+
+    for (int i0 = 1; i0 < n_mel; i0 += kMasPF) {
+#pragma unroll
+        for (int u = 0; u < kMasPF; ++u) {
+            const int i = i0 + u;
+            if (i >= n_mel) break;  // block-uniform
+            const int par = (i - 1) & 1;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                float xv = xr[u][c];
+                {   // refill this ring slot with row i+PF
+                    int r = i + kMasPF;
+                    xr[u][c] = (live[c] && r < n_mel) ? x[(size_t)r * T + col[c]] : 0.f;
+                }
+                if (TAKE_LOG) xv = logf(xv);
+                float left = __shfl_up_sync(0xffffffffu, prev[c], 1);
+                const int g = c * nwarps + warp;  // global warp slot == direction word index
+                if (lane == 0) left = (g == 0) ? NEG_INF : bnd[par][g - 1];
+                const float up = prev[c];
+                // backtrack predicate of alignment.py:68 evaluated for cell (i, col); column 0 never moves
+                const bool diag = (left >= up) && (col[c] >= 1);
+                const uint32_t word = __ballot_sync(0xffffffffu, diag && live[c]);
+                if (lane == 0 && g < W) d[(size_t)i * W + g] = word;
+                const float m = up > left ? up : left;  // max(prev_log1, prev_log2), alignment.py:59
+                const float cur = live[c] ? __fadd_rn(xv, m) : NEG_INF;
+                prev[c] = cur;
+                if (lane == 31) bnd[par ^ 1][g] = cur;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- backtrack (alignment.py:62-73), warp 0, 32 frames per step ----
+    if (warp == 0) {
+        int j = n_text - 1;
+        for (int top = n_mel - 1; top >= 1; top -= 32) {
+            const int row = top - lane;
+            const int wj = j >> 5;
+            uint32_t hi = 0, lo = 0;
+            if (row >= 1) {
+                hi = d[(size_t)row * W + wj];
+                if (wj > 0) lo = d[(size_t)row * W + wj - 1];
+            }
+            const int base = 32 * (wj - 1);  // bit k of (hi:lo) ↔ column base + k
+            int myj = -1;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                if (top - r < 1) break;  // warp-uniform
+                const uint32_t h = __shfl_sync(0xffffffffu, hi, r);
+                const uint32_t l = __shfl_sync(0xffffffffu, lo, r);
+                if (lane == r) myj = j;
+                const int k = j - base;
+                const uint32_t bit = (k >= 32) ? ((h >> (k - 32)) & 1u) : ((l >> k) & 1u);
+                j -= (int)bit;
+            }
+            if (row >= 1) p[row] = myj;
+        }
+        if (lane == 0) p[0] = j;  // opt[0, j] = 1   (alignment.py:73)
+    }
+    __syncthreads();
+    // durations = attn_hard.sum over frames (variance_adaptor.py:267-268)
+    for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
+}
+
+// dense 0/1 map [B,1,F,T] from the per-frame column index: HBM-write bound (4·B·F·T bytes)
+__global__ void __launch_bounds__(256)
+mas_dense_kernel(const int* __restrict__ path, int B, int F, int T, float* __restrict__ hard) {
+    const long rows = (long)B * F;
+    const int lane = threadIdx.x & 31;
+    for (long row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += (long)gridDim.x * (blockDim.x >> 5)) {
+        const int j = path[row];
+        float* o = hard + row * T;
+        if ((T & 3) == 0) {
+            for (int t = lane * 4; t < T; t += 128) {
+                float4 v = make_float4(t == j, t + 1 == j, t + 2 == j, t + 3 == j);
+                st_stream(reinterpret_cast<float4*>(o + t), v);
+            }
+        } else {
+            for (int t = lane; t < T; t += 32) o[t] = (t == j) ? 1.f : 0.f;
+        }
+    }
+}
+
+}  // namespace fs2k
+
+extern "C" size_t fs2k_mas_workspace_bytes(int B, int F, int T) {
+    return (size_t)B * F * ((T + 31) / 32) * sizeof(uint32_t);
+}
+
+extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B,
+                            int F, int T, int* path, int* durations, float* hard, void* workspace,
+                            size_t workspace_bytes, fs2k_stream_t stream) {
+    using namespace fs2k;
+    FS2K_REQUIRE(B >= 0 && F >= 0 && T >= 0, FS2K_ERR_BAD_SHAPE);
+    if (B == 0 || F == 0 || T == 0) return FS2K_OK;
+    FS2K_REQUIRE(T <= 4096, FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(workspace_bytes >= fs2k_mas_workspace_bytes(B, F, T), FS2K_ERR_WORKSPACE);
+    FS2K_REQUIRE(attn && in_lens && out_lens && path && durations && workspace, FS2K_ERR_NULL);
+    const int W = (T + 31) / 32;
+    int threads = ((T < 1024 ? T : 1024) + 31) / 32 * 32;
+    const int chunks = (T + threads - 1) / threads;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* dirs = (uint32_t*)workspace;
+#define LAUNCH(C, L) mas_dp_kernel<C, L><<<B, threads, 0, s>>>(attn, in_lens, out_lens, F, T, W, dirs, path, durations)
+    if (chunks == 1) { if (take_log) LAUNCH(1, true); else LAUNCH(1, false); }
+    else if (chunks == 2) { if (take_log) LAUNCH(2, true); else LAUNCH(2, false); }
+    else { threads = 1024; if (take_log) LAUNCH(4, true); else LAUNCH(4, false); }
+#undef LAUNCH
+    FS2K_CHECK_LAUNCH();
+    if (hard) {
+        const long rows = (long)B * F;
+        int grid = (int)((rows + 7) / 8);
+        if (grid > 148 * 16) grid = 148 * 16;
+        mas_dense_kernel<<<grid, 256, 0, s>>>(path, B, F, T, hard);
+        FS2K_CHECK_LAUNCH();
+    }
+    return FS2K_OK;
+}

@@ -1,0 +1,116 @@
+"""Global style tokens — mirror of reference fs2/gst/model.py:14-280 / gst/attn.py:48-194
+(parameter names kept so checkpoints load).
+
+* `condition_on_gst_tokens` (reference-free synthesis, gst/model.py:77-85): a single key ⇒ the
+  softmax is identically 1 ⇒ linear_out(linear_v(tanh(gst_embs[index]))), two libfs2k GEMMs.
+* `forward(speech)` (reference encoder: 6×Conv2d s2 + BatchNorm2d + ReLU → GRU → 4-head token
+  attention) is SURVEY §8(f) rank 3 — "next", not yet re-kerneled: it currently runs as cuDNN /
+  ATen library calls on the GPU (no CPU path), marked LIBRARY in DESIGN.md.
+"""
+import math
+from collections.abc import Sequence
+
+import torch
+
+from ... import autograd as ag
+
+
+class MultiHeadedAttention(torch.nn.Module):
+    def __init__(self, q_dim, k_dim, v_dim, n_head, n_feat, dropout_rate=0.0):
+        super().__init__()
+        assert n_feat % n_head == 0
+        self.d_k = n_feat // n_head
+        self.h = n_head
+        self.linear_q = torch.nn.Linear(q_dim, n_feat)
+        self.linear_k = torch.nn.Linear(k_dim, n_feat)
+        self.linear_v = torch.nn.Linear(v_dim, n_feat)
+        self.linear_out = torch.nn.Linear(n_feat, n_feat)
+        self.dropout = torch.nn.Dropout(p=dropout_rate)
+
+    def forward(self, query, key, value, mask=None):
+        """LIBRARY path (see module docstring): gst/attn.py:172-194."""
+        B = query.size(0)
+        q = self.linear_q(query).view(B, -1, self.h, self.d_k).transpose(1, 2)
+        k = self.linear_k(key).view(B, -1, self.h, self.d_k).transpose(1, 2)
+        v = self.linear_v(value).view(B, -1, self.h, self.d_k).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(self.d_k)
+        attn = torch.softmax(scores, dim=-1)
+        x = torch.matmul(self.dropout(attn), v).transpose(1, 2).contiguous().view(B, -1, self.h * self.d_k)
+        return self.linear_out(x)
+
+
+class ReferenceEncoder(torch.nn.Module):
+    def __init__(self, idim=80, conv_layers: int = 6, conv_chans_list: Sequence[int] = (32, 32, 64, 64, 128, 128),
+                 conv_kernel_size: int = 3, conv_stride: int = 2, gru_layers: int = 1, gru_units: int = 128):
+        super().__init__()
+        assert conv_kernel_size % 2 == 1, "kernel size must be odd."
+        assert len(conv_chans_list) == conv_layers
+        convs = []
+        padding = (conv_kernel_size - 1) // 2
+        for i in range(conv_layers):
+            conv_in_chans = 1 if i == 0 else conv_chans_list[i - 1]
+            conv_out_chans = conv_chans_list[i]
+            convs += [
+                torch.nn.Conv2d(conv_in_chans, conv_out_chans, kernel_size=conv_kernel_size, stride=conv_stride,
+                                padding=padding, bias=False),
+                torch.nn.BatchNorm2d(conv_out_chans),
+                torch.nn.ReLU(inplace=True),
+            ]
+        self.convs = torch.nn.Sequential(*convs)
+        gru_in_units = idim
+        for _ in range(conv_layers):
+            gru_in_units = (gru_in_units - conv_kernel_size + 2 * padding) // conv_stride + 1
+        gru_in_units *= conv_out_chans
+        self.gru = torch.nn.GRU(gru_in_units, gru_units, gru_layers, batch_first=True)
+
+    def forward(self, speech: torch.Tensor) -> torch.Tensor:
+        """LIBRARY path: gst/model.py:179-199."""
+        batch_size = speech.size(0)
+        hs = self.convs(speech.unsqueeze(1)).transpose(1, 2)
+        hs = hs.contiguous().view(batch_size, hs.size(1), -1)
+        _, ref_embs = self.gru(hs)
+        return ref_embs[-1]
+
+
+class StyleTokenLayer(torch.nn.Module):
+    def __init__(self, ref_embed_dim: int = 128, gst_tokens: int = 10, gst_token_dim: int = 256, gst_heads: int = 4,
+                 dropout_rate: float = 0.0):
+        super().__init__()
+        self.register_parameter("gst_embs", torch.nn.Parameter(torch.randn(gst_tokens, gst_token_dim // gst_heads)))
+        self.mha = MultiHeadedAttention(q_dim=ref_embed_dim, k_dim=gst_token_dim // gst_heads,
+                                        v_dim=gst_token_dim // gst_heads, n_head=gst_heads, n_feat=gst_token_dim,
+                                        dropout_rate=dropout_rate)
+
+    def forward(self, ref_embs: torch.Tensor) -> torch.Tensor:
+        batch_size = ref_embs.size(0)
+        gst_embs = torch.tanh(self.gst_embs).unsqueeze(0).expand(batch_size, -1, -1)
+        return self.mha(ref_embs.unsqueeze(1), gst_embs, gst_embs, None).squeeze(1)
+
+
+class StyleEncoder(torch.nn.Module):
+    def __init__(self, idim: int = 80, gst_tokens: int = 10, gst_token_dim: int = 256, gst_heads: int = 4,
+                 conv_layers: int = 6, conv_chans_list: Sequence[int] = (32, 32, 64, 64, 128, 128),
+                 conv_kernel_size: int = 3, conv_stride: int = 2, gru_layers: int = 1, gru_units: int = 128):
+        super().__init__()
+        self.gst_tokens = gst_tokens
+        self.gst_heads = gst_heads
+        self.gst_token_dim = gst_token_dim
+        self.ref_enc = ReferenceEncoder(idim=idim, conv_layers=conv_layers, conv_chans_list=conv_chans_list,
+                                        conv_kernel_size=conv_kernel_size, conv_stride=conv_stride,
+                                        gru_layers=gru_layers, gru_units=gru_units)
+        self.stl = StyleTokenLayer(ref_embed_dim=gru_units, gst_tokens=gst_tokens, gst_token_dim=gst_token_dim,
+                                   gst_heads=gst_heads)
+
+    def condition_on_gst_tokens(self, batch_size, index=0):
+        if index >= self.gst_tokens:
+            raise ValueError(f"We can only synthesize by conditioning on one of {self.gst_tokens} GST tokens")
+        from ... import autograd_fns as fns
+
+        mha = self.stl.mha
+        g = fns.tanh_row(self.stl.gst_embs, index)  # [1, token_dim/heads]
+        v = ag.linear(g, mha.linear_v.weight, mha.linear_v.bias)
+        o = ag.linear(v, mha.linear_out.weight, mha.linear_out.bias)  # [1, token_dim]
+        return o.expand(batch_size, -1)
+
+    def forward(self, speech: torch.Tensor) -> torch.Tensor:
+        return self.stl(self.ref_enc(speech))

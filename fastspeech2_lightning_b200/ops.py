@@ -1,0 +1,423 @@
+"""Tensor-level wrappers over the libfs2k C ABI.
+
+PyTorch is used for device memory and streams only: every function takes CUDA tensors,
+allocates its outputs with `torch.empty`, and enqueues hand-written sm_100a kernels on the
+current stream.  Nothing here computes with torch ops; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import check, lib
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3
+_ACTS = {None: 0, "none": 0, "relu": 1, "silu": 2, "tanh": 3}
+
+# count of kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i32(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# ---------------------------------------------------------------------------------------------
+# monotonic alignment search
+# ---------------------------------------------------------------------------------------------
+def mas(attn: torch.Tensor, in_lens: torch.Tensor, out_lens: torch.Tensor, take_log: bool = False, dense: bool = True):
+    """attn [B,1,F,T] or [B,F,T] (log-probs, or probs with take_log) → (path [B,F] i32, durations [B,T] i32,
+    hard [B,1,F,T] f32 or None)."""
+    a = _f32(attn, "attn")
+    if a.dim() == 4:
+        assert a.shape[1] == 1
+        B, _, F, T = a.shape
+    else:
+        B, F, T = a.shape
+    il, ol = _i32(in_lens, "in_lens"), _i32(out_lens, "out_lens")
+    path = torch.empty((B, F), dtype=torch.int32, device=a.device)
+    dur = torch.empty((B, T), dtype=torch.int32, device=a.device)
+    hard = torch.empty((B, 1, F, T), dtype=torch.float32, device=a.device) if dense else None
+    ws_bytes = lib().fs2k_mas_workspace_bytes(B, F, T)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=a.device)
+    check(lib().fs2k_mas_fwd(_p(a), int(take_log), _p(il), _p(ol), B, F, T, _p(path), _p(dur), _p(hard), _p(ws), ws_bytes, _stream()), "fs2k_mas_fwd")
+    _count(2 if dense else 1)
+    return path, dur, hard
+
+
+# ---------------------------------------------------------------------------------------------
+# length regulator
+# ---------------------------------------------------------------------------------------------
+def lr_scan(durations: torch.Tensor):
+    d = _i32(durations, "durations")
+    B, T = d.shape
+    cum = torch.empty_like(d)
+    total = torch.empty((B,), dtype=torch.int32, device=d.device)
+    check(lib().fs2k_lr_scan(_p(d), B, T, _p(cum), _p(total), _stream()), "fs2k_lr_scan")
+    _count()
+    return cum, total
+
+
+def lr_gather(x, cum, total, f_out: int, inv_freq: Optional[torch.Tensor] = None, want_out=True, want_idx=False):
+    x = _f32(x, "x")
+    B, T, D = x.shape
+    dev = x.device
+    out = torch.empty((B, f_out, D), dtype=torch.float32, device=dev) if want_out else None
+    out_pos = torch.empty((B, f_out, D), dtype=torch.float32, device=dev) if inv_freq is not None else None
+    mask = torch.empty((B, f_out), dtype=torch.bool, device=dev)
+    idx = torch.empty((B, f_out), dtype=torch.int32, device=dev) if want_idx else None
+    check(lib().fs2k_lr_gather(_p(x), _p(cum), _p(total), B, T, D, f_out, _p(out), _p(out_pos), _p(inv_freq), _p(mask), _p(idx), _stream()), "fs2k_lr_gather")
+    _count()
+    return out, out_pos, mask, idx
+
+
+# ---------------------------------------------------------------------------------------------
+# variance adaptor pieces
+# ---------------------------------------------------------------------------------------------
+def bucketize_embed_add(v, bins, table, x, scale: float = 1.0, want_ids=True, want_scaled=False):
+    v, bins, table, x = _f32(v, "v"), _f32(bins, "bins"), _f32(table, "table"), _f32(x, "x")
+    N, D = v.numel(), x.shape[-1]
+    assert x.numel() == N * D and table.shape[1] == D and table.shape[0] >= bins.numel() + 1
+    y = torch.empty_like(x)
+    ids = torch.empty(v.shape, dtype=torch.int64, device=v.device) if want_ids else None
+    vs = torch.empty_like(v) if want_scaled else None
+    check(lib().fs2k_bucketize_embed_add(_p(v), float(scale), _p(vs), _p(bins), bins.numel(), _p(table), _p(x), _p(y), _p(ids), N, D, _stream()), "fs2k_bucketize_embed_add")
+    _count()
+    return y, ids, vs
+
+
+def bucketize(v, bins):
+    v, bins = _f32(v, "v"), _f32(bins, "bins")
+    ids = torch.empty(v.shape, dtype=torch.int64, device=v.device)
+    check(lib().fs2k_bucketize(_p(v), _p(bins), bins.numel(), _p(ids), v.numel(), _stream()), "fs2k_bucketize")
+    _count()
+    return ids
+
+
+def average_variance(var, cum):
+    var = _f32(var, "var")
+    B, F = var.shape
+    T = cum.shape[1]
+    out = torch.empty((B, T), dtype=torch.float32, device=var.device)
+    check(lib().fs2k_average_variance(_p(var), _p(cum), B, F, T, _p(out), _stream()), "fs2k_average_variance")
+    _count()
+    return out
+
+
+def round_durations(log_dur, control: float = 1.0):
+    ld = _f32(log_dur, "log_dur")
+    dur = torch.empty(ld.shape, dtype=torch.int32, device=ld.device)
+    check(lib().fs2k_round_durations(_p(ld), float(control), ld.numel(), _p(dur), _stream()), "fs2k_round_durations")
+    _count()
+    return dur
+
+
+def embed_posenc(text, table, inv_freq, lens, want_emb=True):
+    text, table, inv_freq, lens = _i32(text, "text"), _f32(table, "table"), _f32(inv_freq, "inv_freq"), _i32(lens, "lens")
+    B, T = text.shape
+    D = table.shape[1]
+    emb = torch.empty((B, T, D), dtype=torch.float32, device=table.device) if want_emb else None
+    x = torch.empty((B, T, D), dtype=torch.float32, device=table.device)
+    check(lib().fs2k_embed_posenc(_p(text), _p(table), table.shape[0], _p(inv_freq), _p(lens), B, T, D, _p(emb), _p(x), None, _stream()), "fs2k_embed_posenc")
+    _count()
+    return emb, x
+
+
+def add_posenc(x, inv_freq, lens):
+    x, inv_freq, lens = _f32(x, "x"), _f32(inv_freq, "inv_freq"), _i32(lens, "lens")
+    B, L, D = x.shape
+    y = torch.empty_like(x)
+    check(lib().fs2k_add_posenc(_p(x), _p(inv_freq), _p(lens), B, L, D, _p(y), _stream()), "fs2k_add_posenc")
+    _count()
+    return y
+
+
+def add_rows(x, rows_and_ids):
+    """x [B,L,D] + Σ rows[ids[b]] for up to three (rows [R,D], ids [B] int32 or None) pairs."""
+    x = _f32(x, "x")
+    B, L, D = x.shape
+    y = torch.empty_like(x)
+    args = []
+    keep = []
+    for rows, ids in list(rows_and_ids) + [(None, None)] * (3 - len(rows_and_ids)):
+        if rows is not None:
+            rows = _f32(rows, "rows")
+            ids = _i32(ids, "ids") if ids is not None else None
+            keep += [rows, ids]
+        args += [_p(rows), _p(ids)]
+    check(lib().fs2k_add_rows(_p(x), _p(y), B, L, D, *args, _stream()), "fs2k_add_rows")
+    _count()
+    return y
+
+
+def lens_mask(lens, max_len: int):
+    lens = _i32(lens, "lens")
+    B = lens.shape[0]
+    mask = torch.empty((B, int(max_len)), dtype=torch.bool, device=lens.device)
+    check(lib().fs2k_lens_mask(_p(lens), B, int(max_len), _p(mask), _stream()), "fs2k_lens_mask")
+    _count()
+    return mask
+
+
+def mask_lens(mask):
+    assert mask.is_cuda and mask.dtype in (torch.bool, torch.uint8)
+    m = mask.contiguous()
+    B, L = m.shape
+    lens = torch.empty((B,), dtype=torch.int32, device=m.device)
+    check(lib().fs2k_mask_lens(_p(m), B, L, _p(lens), _stream()), "fs2k_mask_lens")
+    _count()
+    return lens
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------
+def layernorm(x, gamma, beta, eps: float = 1e-5, save_stats: bool = False):
+    x = _f32(x, "x")
+    D = x.shape[-1]
+    M = x.numel() // D
+    y = torch.empty_like(x)
+    mean = torch.empty((M,), dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device) if save_stats else None
+    check(lib().fs2k_layernorm_fwd(_p(x), _p(_f32(gamma)), _p(_f32(beta)), float(eps), M, D, _p(y), _p(mean), _p(rstd), _stream()), "fs2k_layernorm_fwd")
+    _count()
+    return (y, mean, rstd) if save_stats else y
+
+
+def bn_scale_shift(bn: torch.nn.modules.batchnorm._BatchNorm, z: Optional[torch.Tensor], training: bool, save_stats=False):
+    """(scale, shift) of a BatchNorm layer: batch statistics of z[M,C] (and running-stat update) when
+    training, folded running statistics otherwise."""
+    C = bn.num_features
+    dev = bn.weight.device
+    scale = torch.empty((C,), dtype=torch.float32, device=dev)
+    shift = torch.empty((C,), dtype=torch.float32, device=dev)
+    save_mean = torch.empty((C,), dtype=torch.float32, device=dev) if save_stats else None
+    save_rstd = torch.empty((C,), dtype=torch.float32, device=dev) if save_stats else None
+    sums = None
+    M = 0
+    if training:
+        z = _f32(z, "z")
+        M = z.numel() // C
+        sums = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+        check(lib().fs2k_colstats(_p(z), M, C, _p(sums), _stream()), "fs2k_colstats")
+        _count()
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    check(lib().fs2k_bn_finalize(_p(sums), M, C, _p(bn.weight), _p(bn.bias), float(bn.eps), float(momentum), int(training),
+                                 _p(bn.running_mean), _p(bn.running_var), _p(bn.num_batches_tracked) if training else None,
+                                 _p(scale), _p(shift), _p(save_mean), _p(save_rstd), _stream()), "fs2k_bn_finalize")
+    _count()
+    if save_stats:
+        return scale, shift, save_mean, save_rstd
+    return scale, shift
+
+
+def affine_act(z, scale, shift, act=None, residual=None):
+    z = _f32(z, "z")
+    C = z.shape[-1]
+    M = z.numel() // C
+    y = torch.empty_like(z)
+    check(lib().fs2k_affine_act(_p(z), _p(scale), _p(shift), _ACTS[act], _p(residual), M, C, _p(y), _stream()), "fs2k_affine_act")
+    _count()
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# dense contractions
+# ---------------------------------------------------------------------------------------------
+_repack_cache: dict = {}
+
+
+def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight [N,K,taps] → [taps,N,K] (cached per weight version; 1-tap weights are a view)."""
+    N, K, taps = weight.shape
+    if taps == 1:
+        return weight.detach().reshape(1, N, K)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _repack_cache.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    w = _f32(weight.detach(), "weight")
+    out = torch.empty((taps, N, K), dtype=torch.float32, device=w.device)
+    check(lib().fs2k_repack_conv_weight(_p(w), N, K, taps, _p(out), _stream()), "fs2k_repack_conv_weight")
+    _count()
+    _repack_cache[id(weight)] = (key, out)
+    return out
+
+
+def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,
+         residual=None, row_mask=None, out=None):
+    """a [B,L,K] (or [M,K]) · w [taps,N,K] or [N,K] with the fused epilogue of fs2k_gemm_f32."""
+    a = _f32(a, "a")
+    if a.dim() == 2:
+        B, L, K = 1, a.shape[0], a.shape[1]
+        out_shape = (L,)
+    else:
+        B, L, K = a.shape
+        out_shape = (B, L)
+    w = _f32(w, "w")
+    if w.dim() == 2:
+        w = w.reshape(1, *w.shape)
+    taps, N, Kw = w.shape
+    assert Kw == K, (Kw, K)
+    c = out if out is not None else torch.empty((*out_shape, N), dtype=torch.float32, device=a.device)
+    if residual is not None:
+        residual = _f32(residual, "residual")
+    if row_mask is not None:
+        row_mask = row_mask.contiguous()
+        assert row_mask.dtype in (torch.bool, torch.uint8)
+    check(lib().fs2k_gemm_f32(_p(a), K, B, L, K, _p(w), N, taps, taps_pad, _p(bias), _p(scale), _p(shift), _ACTS[act],
+                              float(alpha), _p(residual), N, _p(row_mask), _p(c), N, _stream()), "fs2k_gemm_f32")
+    _count()
+    return c
+
+
+def rowdot(x, w, b=None, mask=None):
+    x = _f32(x, "x")
+    D = x.shape[-1]
+    M = x.numel() // D
+    y = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    if mask is not None:
+        mask = mask.contiguous()
+    check(lib().fs2k_rowdot(_p(x), _p(_f32(w)), _p(b), _p(mask), M, D, _p(y), _stream()), "fs2k_rowdot")
+    _count()
+    return y
+
+
+def attention(qkv, lens, heads: int, want_lse: bool = False):
+    qkv, lens = _f32(qkv, "qkv"), _i32(lens, "lens")
+    B, L, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, L, D), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((B, heads, L), dtype=torch.float32, device=qkv.device) if want_lse else None
+    check(lib().fs2k_attention_f32(_p(qkv), _p(lens), B, L, heads, D // heads, _p(out), _p(lse), _stream()), "fs2k_attention_f32")
+    _count()
+    return (out, lse) if want_lse else out
+
+
+def dwconv(x, weight, bias, *, channels: int, glu: bool = False, scale=None, shift=None):
+    """x [B,L,ldx] → [B,L,channels]; weight [C,1,K]."""
+    x = _f32(x, "x")
+    B, L, ldx = x.shape
+    K = weight.shape[-1]
+    y = torch.empty((B, L, channels), dtype=torch.float32, device=x.device)
+    check(lib().fs2k_dwconv_fwd(_p(x), ldx, B, L, channels, _p(_f32(weight)), K, _p(bias), int(glu), _p(scale), _p(shift), _p(y), _stream()), "fs2k_dwconv_fwd")
+    _count()
+    return y
+
+
+def aligner_scores(q, k, prior, key_lens):
+    q, k = _f32(q, "q"), _f32(k, "k")
+    B, F, C = q.shape
+    T = k.shape[1]
+    if prior is not None:
+        prior = _f32(prior, "prior")
+        assert prior.shape == (B, F, T), (prior.shape, (B, F, T))
+    logprob = torch.empty((B, 1, F, T), dtype=torch.float32, device=q.device)
+    soft = torch.empty((B, 1, F, T), dtype=torch.float32, device=q.device)
+    kl = _i32(key_lens, "key_lens") if key_lens is not None else None
+    check(lib().fs2k_aligner_fwd(_p(q), _p(k), _p(prior), _p(kl), B, F, T, C, _p(logprob), _p(soft), _stream()), "fs2k_aligner_fwd")
+    _count(2)
+    return soft, logprob
+
+
+# ---------------------------------------------------------------------------------------------
+# losses and small elementwise helpers
+# ---------------------------------------------------------------------------------------------
+_KIND = {"mse": 0, "mae": 1}
+
+
+def masked_loss_fwd(pred, target, row_mask, kind: str, weight: float, log1p_int_target: bool = False):
+    pred = _f32(pred, "pred")
+    target = _i32(target, "target") if log1p_int_target else _f32(target, "target")
+    row_mask = row_mask.contiguous()
+    M = row_mask.numel()
+    C = pred.numel() // max(M, 1)
+    assert pred.numel() == target.numel() == M * C, (pred.shape, target.shape, row_mask.shape)
+    scratch = torch.empty((1,), dtype=torch.float64, device=pred.device)
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    check(lib().fs2k_masked_loss_fwd(_p(pred), _p(target), int(log1p_int_target), _p(row_mask), M, C, _KIND[kind], float(weight), _p(scratch), _p(loss), _stream()), "fs2k_masked_loss_fwd")
+    _count(2)
+    return loss
+
+
+def masked_loss_bwd(pred, target, row_mask, kind: str, weight: float, gout, log1p_int_target: bool = False):
+    pred = _f32(pred, "pred")
+    target = _i32(target, "target") if log1p_int_target else _f32(target, "target")
+    row_mask = row_mask.contiguous()
+    M = row_mask.numel()
+    C = pred.numel() // max(M, 1)
+    dpred = torch.empty_like(pred)
+    check(lib().fs2k_masked_loss_bwd(_p(pred), _p(target), int(log1p_int_target), _p(row_mask), M, C, _KIND[kind], float(weight), _p(_f32(gout)), _p(dpred), _stream()), "fs2k_masked_loss_bwd")
+    _count()
+    return dpred
+
+
+def bin_loss_fwd(hard, soft, eps: float):
+    hard, soft = _f32(hard, "hard"), _f32(soft, "soft")
+    sums = torch.empty((2,), dtype=torch.float64, device=soft.device)
+    loss = torch.empty((), dtype=torch.float32, device=soft.device)
+    check(lib().fs2k_bin_loss_fwd(_p(hard), _p(soft), soft.numel(), float(eps), _p(sums), _p(loss), _stream()), "fs2k_bin_loss_fwd")
+    _count(2)
+    return loss, sums
+
+
+def bin_loss_bwd(hard, soft, eps: float, sums, gout):
+    dsoft = torch.empty_like(soft)
+    check(lib().fs2k_bin_loss_bwd(_p(hard), _p(soft), soft.numel(), float(eps), _p(sums), _p(_f32(gout)), _p(dsoft), _stream()), "fs2k_bin_loss_bwd")
+    _count()
+    return dsoft
+
+
+def axpby(a, alpha: float, b=None, beta: float = 0.0):
+    a = _f32(a, "a")
+    if b is not None:
+        b = _f32(b, "b")
+        assert b.shape == a.shape, (a.shape, b.shape)
+    out = torch.empty_like(a)
+    check(lib().fs2k_axpby(_p(a), float(alpha), _p(b), float(beta), a.numel(), _p(out), _stream()), "fs2k_axpby")
+    _count()
+    return out
+
+
+def gather_rows(table, ids):
+    table = _f32(table, "table")
+    ids = ids.contiguous()
+    assert ids.dtype == torch.int64
+    out = torch.empty((*ids.shape, table.shape[1]), dtype=torch.float32, device=table.device)
+    check(lib().fs2k_gather_rows(_p(table), _p(ids), ids.numel(), table.shape[1], _p(out), _stream()), "fs2k_gather_rows")
+    _count()
+    return out
+
+
+def tanh(x):
+    x = _f32(x, "x")
+    y = torch.empty_like(x)
+    check(lib().fs2k_tanh(_p(x), x.numel(), _p(y), _stream()), "fs2k_tanh")
+    _count()
+    return y

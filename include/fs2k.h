@@ -1,0 +1,163 @@
+/* libfs2k — C ABI of the B200 (sm_100a) kernels behind the FastSpeech2 acoustic-model hot path.
+ *
+ * The reference (EveryVoiceTTS/FastSpeech2_lightning) has no FFI of its own: the seam is plain
+ * Python `nn.Module` classes.  Each entry point below replaces the PyTorch library
+ * calls at the cited reference lines; the Python mirror package `fastspeech2_lightning_b200.fs2`
+ * binds them with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - activations are channels-last fp32 `[B, L, C]`, contiguous; lengths/durations int32;
+ *     bucket ids int64 (to match torch.bucketize); boolean masks uint8
+ *   - no allocation, no synchronisation, no host<->device copy inside; work is enqueued on `stream`
+ *   - returns FS2K_OK (0) or a negative FS2K_ERR_* code; never aborts; fs2k_strerror() explains
+ *   - `[B,L]` pairs describe the row space: row m = b·L + l; convolution taps never cross b
+ */
+#ifndef FS2K_H_
+#define FS2K_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fs2k_stream_t; /* a cudaStream_t */
+
+enum {
+    FS2K_OK = 0,
+    FS2K_ERR_BAD_SHAPE = -1,
+    FS2K_ERR_UNSUPPORTED = -2,
+    FS2K_ERR_WORKSPACE = -3,
+    FS2K_ERR_NULL = -4,
+    FS2K_ERR_CUDA = -5,
+    FS2K_ERR_ARCH = -6
+};
+
+enum { FS2K_ACT_NONE = 0, FS2K_ACT_RELU = 1, FS2K_ACT_SILU = 2, FS2K_ACT_TANH = 3 };
+
+const char* fs2k_strerror(int code);
+int fs2k_version(void);
+int fs2k_check_device(void); /* FS2K_OK iff the current device is compute capability 10.x */
+
+/* ---- monotonic alignment search -------------------------------------------------------------
+ * replaces VarianceAdaptor.binarize_attention (fs2/variance_adaptor.py:160-181) and
+ * mas_width1 / b_mas (fs2/attn/alignment.py:48-85).
+ * attn [B,F,T]: log-probabilities, or probabilities when take_log != 0 (the `torch.log` of :168 fused).
+ * out: path [B,F] int32 (text index of every mel frame, -1 on padded frames), durations [B,T] int32
+ * (= attn_hard.sum(2), :267-268), hard [B,1,F,T] fp32 0/1 (may be NULL).  T <= 4096. */
+size_t fs2k_mas_workspace_bytes(int B, int F, int T);
+int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B, int F, int T,
+                 int* path, int* durations, float* hard, void* workspace, size_t workspace_bytes,
+                 fs2k_stream_t stream);
+
+/* ---- LengthRegulator (fs2/variance_adaptor.py:65-81) ------------------------------------------
+ * scan:   cum[b,t] = inclusive cumsum of max(dur,0); total[b] = cum[b,T-1]
+ * gather: out[b,f,:] = f < total[b] ? x[b, #{t: cum[b,t] <= f}, :] : 0 ; mask[b,f] = f < total[b];
+ *         out_pos (optional) = out + PositionalEmbedding(f)·mask  (fs2/model.py:233-241 fused);
+ *         idx_out (optional) = the gather index, -1 on padding.  F_out is the caller's
+ *         min(max_b total, max_length). */
+int fs2k_lr_scan(const int* durations, int B, int T, int* cum, int* total, fs2k_stream_t stream);
+int fs2k_lr_gather(const float* x, const int* cum, const int* total, int B, int T, int D, int F_out, float* out,
+                   float* out_pos, const float* inv_freq, uint8_t* mask, int* idx_out, fs2k_stream_t stream);
+
+/* ---- variance embedding (fs2/variance_adaptor.py:183-205,:322,:343) ---------------------------
+ * ids = torch.bucketize(v·scale, bins) (right=False; NaN -> n_bins); y = x + table[ids].
+ * v_scaled (optional) receives v·scale (the `prediction * control` of :202). y may alias x. */
+int fs2k_bucketize_embed_add(const float* v, float scale, float* v_scaled, const float* bins, int n_bins,
+                             const float* table, const float* x, float* y, long long* ids, long N, int D,
+                             fs2k_stream_t stream);
+int fs2k_bucketize(const float* v, const float* bins, int n_bins, long long* ids, long N, fs2k_stream_t stream);
+
+/* average_variance (fs2/variance_adaptor.py:207-222): per phone mean of the non-zero frame values
+ * inside its duration span; cum is the inclusive cumsum from fs2k_lr_scan. */
+int fs2k_average_variance(const float* var, const int* cum, int B, int F, int T, float* out, fs2k_stream_t stream);
+
+/* inference duration rounding (fs2/variance_adaptor.py:359-366):
+ * dur = int(clamp(rint(exp(log_dur) - 1) * control, min=0)) */
+int fs2k_round_durations(const float* log_dur, float control, long N, int* dur, fs2k_stream_t stream);
+
+/* ---- embeddings (fs2/model.py:183-213, fs2/layers.py:132-140) ---------------------------------
+ * emb = table[text] (optional output: the aligner's keys); x = emb + PositionalEmbedding(t)·[t < lens[b]].
+ * err_flag (optional) is set to 1 when an id is outside [0, n_sym). */
+int fs2k_embed_posenc(const int* text, const float* table, int n_sym, const float* inv_freq, const int* lens, int B,
+                      int T, int D, float* emb, float* x, int* err_flag, fs2k_stream_t stream);
+int fs2k_add_posenc(const float* x_in, const float* inv_freq, const int* lens, int B, int L, int D, float* x,
+                    fs2k_stream_t stream);
+/* y[b,l,:] = x[b,l,:] + sum_k rows_k[ids_k ? ids_k[b] : b, :]  (GST / speaker / language rows) */
+int fs2k_add_rows(const float* x, float* y, int B, int L, int D, const float* rows0, const int* ids0,
+                  const float* rows1, const int* ids1, const float* rows2, const int* ids2, fs2k_stream_t stream);
+/* mask[b,l] = l < lens[b]  (mask_from_lens, fs2/utils/heavy.py:11-15) */
+int fs2k_lens_mask(const int* lens, int B, int L, uint8_t* mask, fs2k_stream_t stream);
+/* lens[b] = count_nonzero(mask[b,:])  (fs2/model.py:226-230) */
+int fs2k_mask_lens(const uint8_t* mask, int B, int L, int* lens, fs2k_stream_t stream);
+
+/* ---- normalisation ------------------------------------------------------------------------------
+ * LayerNorm over the last dim (eps 1e-5): torchaudio conformer.py:41,103,151,165; fs2/layers.py:42.
+ * mean_out / rstd_out (optional, [M]) are saved for the backward pass. */
+int fs2k_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, long M, int D, float* y,
+                       float* mean_out, float* rstd_out, fs2k_stream_t stream);
+/* BatchNorm1d (conformer.py:62-64, fs2/layers.py:168-202): colstats = per-channel sum / sum-of-squares of
+ * z[M,C] in fp64 (sums[2C], zeroed here); bn_finalize turns them (training) or the running stats (eval)
+ * into scale/shift and, in training, updates running_mean/var (momentum, unbiased var) in place. */
+int fs2k_colstats(const float* z, long M, int C, double* sums, fs2k_stream_t stream);
+int fs2k_bn_finalize(const double* sums, long M, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, int training, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float* scale, float* shift, float* save_mean, float* save_rstd,
+                     fs2k_stream_t stream);
+/* y = act(z*scale[c] + shift[c]) (+ residual) */
+int fs2k_affine_act(const float* z, const float* scale, const float* shift, int act, const float* residual, long M,
+                    int C, float* y, fs2k_stream_t stream);
+
+/* ---- dense contractions ---------------------------------------------------------------------------
+ * C[(b,l),n] = (act((sum_tap sum_k A[b,l+tap-pad,k] W[tap][n][k] + bias[n]) * scale[n] + shift[n]) * alpha
+ *               + residual[(b,l),n]) * row_mask[(b,l)]
+ * = nn.Linear / Conv1d(k) on channels-last data with the following elementwise ops fused.
+ * W is [taps][N][K] (fs2k_repack_conv_weight converts PyTorch's [N][K][taps]).
+ * fs2k_gemm_f32: exact fp32 FFMA path.  fs2k_gemm_tc (gemm_tc.cu): tcgen05 tensor-core path. */
+int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
+                  const float* bias, const float* scale, const float* shift, int act, float alpha,
+                  const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, fs2k_stream_t stream);
+int fs2k_rowdot(const float* x, const float* w, const float* b, const uint8_t* mask, long M, int D, float* y,
+                fs2k_stream_t stream);
+int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
+
+/* ---- attention (torchaudio conformer.py:151-153,193-202) ------------------------------------------
+ * qkv [B,L,3·H·hd] packed in_proj output; out [B,L,H·hd]; keys >= lens[b] masked; lse_out optional [B,H,L]. */
+int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float* out,
+                       float* lse_out, fs2k_stream_t stream);
+
+/* ---- depthwise conv (conformer.py:50-65 with GLU/BatchNorm/SiLU fused; fs2/blocks.py:8-15) ---------
+ * x [B,L,ldx] (glu: value c, gate c+C); w [C][K]; scale/shift non-NULL: y = silu((conv+bias)*scale+shift). */
+int fs2k_dwconv_fwd(const float* x, int ldx, int B, int L, int C, const float* w, int K, const float* bias, int glu,
+                    const float* scale, const float* shift, float* y, fs2k_stream_t stream);
+
+/* ---- aligner scores (fs2/attn/attention.py:238-251) -------------------------------------------------
+ * q [B,F,C], k [B,T,C] projected queries/keys; prior [B,F,T] or NULL; logprob, soft [B,F,T]. */
+int fs2k_aligner_fwd(const float* q, const float* k, const float* prior, const int* key_lens, int B, int F, int T,
+                     int C, float* logprob, float* soft, fs2k_stream_t stream);
+
+/* ---- losses (fs2/loss.py:44-106, fs2/attn/attention_loss.py:65-73) ----------------------------------
+ * masked_loss: loss = weight · mean_{all M·C elements} f(pred·m − target·m), f = square (kind 0) or abs (1),
+ * m = row_mask[M]; target_is_int_log1p: target is int32 and enters as log(target + 1) (duration loss).
+ * scratch: one double (fwd).  bwd: dpred = gout · weight/N · f'(...) · m. */
+int fs2k_masked_loss_fwd(const float* pred, const void* target, int target_is_int_log1p, const uint8_t* row_mask,
+                         long M, int C, int kind, float weight, double* scratch, float* loss, fs2k_stream_t stream);
+int fs2k_masked_loss_bwd(const float* pred, const void* target, int target_is_int_log1p, const uint8_t* row_mask,
+                         long M, int C, int kind, float weight, const float* gout, float* dpred, fs2k_stream_t stream);
+/* bin loss = −Σ_{hard==1} log(max(soft, eps)) / Σ hard ; sums[2] doubles are kept for the backward */
+int fs2k_bin_loss_fwd(const float* hard, const float* soft, long N, float eps, double* sums, float* loss,
+                      fs2k_stream_t stream);
+int fs2k_bin_loss_bwd(const float* hard, const float* soft, long N, float eps, const double* sums, const float* gout,
+                      float* dsoft, fs2k_stream_t stream);
+
+/* ---- small elementwise helpers ------------------------------------------------------------------------ */
+int fs2k_axpby(const float* a, float alpha, const float* b, float beta, long N, float* out, fs2k_stream_t stream);
+int fs2k_gather_rows(const float* table, const long long* ids, long R, int D, float* out, fs2k_stream_t stream);
+int fs2k_tanh(const float* x, long N, float* y, fs2k_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2K_H_ */
