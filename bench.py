@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the FastSpeech2 acoustic-model hot path on B200 (contract: see DESIGN.md §measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload synth_c1|synth_c4|mas_c2|mas_c5]
+    python bench.py --impl reference ...     # the reference's CPU arithmetic (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch.
+`value` is device-timed with the inputs resident in HBM; `e2e` goes through the public module API
+(`FastSpeech2.predict_step`) with pinned-host inputs copied in and the mel copied out inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: base config, teacher-forced synthesis, B=16, T≈80 → F≈500
+    "synth_c1": dict(kind="synth", batch=16, src=(60, 80), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
+    # configs[3]: 256 utterances of 20-200 phonemes in length-sorted batches of 32 (one step = one batch of 32)
+    "synth_c4": dict(kind="synth", batch=32, src=(20, 200), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
+    "mas_c2": dict(kind="mas", batch=32, F=500, T=80, metric="mas_ms_per_batch", unit="ms/batch"),
+    "mas_c5": dict(kind="mas", batch=1, F=8000, T=1000, metric="mas_ms_per_batch", unit="ms/batch"),
+}
+
+
+def flops_fwd(B, T, F, aligner=False):
+    """forward FLOPs on the padded B×L rectangle."""
+    f = 4 * T * (3_019_264 + 1024 * T) + 4 * F * (3_019_264 + 1024 * F) + 3 * T * 663_552 + F * 40_960 + F * 8_683_520
+    if aligner:
+        f += T * 868_352 + F * 115_200 + F * T * 240
+    return B * f
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(wl, device):
+    from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.fs2.config import FastSpeech2Config
+    from fastspeech2_lightning_b200.fs2.model import FastSpeech2
+
+    cfg = FastSpeech2Config(model=dict(learn_alignment=wl["learn_alignment"]))
+    torch.manual_seed(1234)
+    model = FastSpeech2(cfg, stats=synthetic.DEFAULT_STATS)  # random init of the reference architecture
+    model.eval()
+    if device is not None:
+        model = model.to(device)
+        if model.variance_adaptor is not None:
+            model.variance_adaptor.validate_durations = False
+    return cfg, model
+
+
+def make_batches(wl, n, rank):
+    from fastspeech2_lightning_b200 import synthetic
+
+    out = []
+    for i in range(n):
+        b = synthetic.make_batch(wl["batch"], wl["src"], seed=1234 + 1000 * rank + i, learn_alignment=wl["learn_alignment"],
+                                 inference=True, teacher_forced=True)
+        out.append(b)
+    return out
+
+
+def pin(batch):
+    return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def batch_bytes(batch):
+    return sum(v.numel() * v.element_size() for v in batch.values() if torch.is_tensor(v))
+
+
+def kernel_work(name, args):
+    """(flops, bytes) of one C-ABI call, from its arguments (DESIGN.md lists the formulas)."""
+    if name == "fs2k_gemm_f32" or name == "fs2k_gemm_tc":
+        B, L, K, N, taps = args[2], args[3], args[4], args[6], args[7]
+        return 2.0 * B * L * K * N * taps, 4.0 * (B * L * (K + N) + N * K * taps)
+    if name == "fs2k_attention_f32":
+        B, L, H, hd = args[2], args[3], args[4], args[5]
+        return 4.0 * B * H * L * L * hd, 4.0 * B * L * 4 * H * hd
+    if name == "fs2k_mas_fwd":
+        B, F, T = args[4], args[5], args[6]
+        return 0.0, 8.0 * B * F * T
+    if name == "fs2k_lr_gather":
+        B, T, D, F = args[3], args[4], args[5], args[6]
+        return 0.0, 4.0 * B * D * (T + F * (2 if args[8] else 1)) + 4.0 * B * T
+    return 0.0, 0.0
+
+
+def run_ours(args, wl_name, wl, rank, world, device):
+    from fastspeech2_lightning_b200 import _lib, ops, synthetic
+
+    pk = peaks()
+    n_distinct = 4
+    if wl["kind"] == "mas":
+        return run_mas(args, wl_name, wl, rank, world, device, pk)
+    cfg, model = build_model(wl, device)
+    host_batches = [pin(b) for b in make_batches(wl, n_distinct, rank)]
+    dev_batches = [synthetic.batch_to(b, device) for b in host_batches]
+    frames = [int(b["mel_lens"].sum()) for b in host_batches]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def step(i):
+        with torch.no_grad():
+            return model(dev_batches[i % n_distinct], inference=True)
+
+    def step_e2e(i):
+        hb = host_batches[i % n_distinct]
+        out = model.predict_step(synthetic.batch_to(hb, device, non_blocking=True), i)
+        mel = out[model.output_key].to("cpu", non_blocking=False)
+        lens = out["tgt_lens"].cpu()
+        return mel, lens
+
+    for i in range(args.warmup):
+        step(i)
+        step_e2e(i)
+    torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.fill_(i & 1)  # evict L2 between timed iterations (outside the event pair)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    launches0 = ops.launch_count
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        ms_dev = timed(step, args.steps)
+        launches = ops.launch_count - launches0
+        ms_e2e = timed(step_e2e, args.steps)
+    total_frames = sum(frames[i % n_distinct] for i in range(args.steps))
+
+    # roofline pass: the same steps with every C-ABI call bracketed by CUDA events on the launch stream
+    _lib.start_profile()
+    for i in range(min(args.steps, 4)):
+        step(i)
+    recs = _lib.stop_profile()
+    by = {}
+    for name, a, ms in recs:
+        f, b = kernel_work(name, a)
+        d = by.setdefault(name, [0.0, 0.0, 0.0, 0])
+        d[0] += ms; d[1] += f; d[2] += b; d[3] += 1
+    tot_ms = sum(d[0] for d in by.values())
+    dom = max(by, key=lambda k: by[k][0])
+    d = by[dom]
+    if d[1] > 0:
+        roof = {"kernel": dom, "bound": "tensor", "achieved": d[1] / (d[0] * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=pk["source"], share_of_step=d[0] / tot_ms,
+                launches=d[3], shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])})
+
+    # max over ranks, whole-job aggregate
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
+    n = torch.tensor([float(total_frames)], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(n, op=torch.distributed.ReduceOp.SUM)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    all_frames = float(n[0])
+    B, T, F = wl["batch"], int(host_batches[0]["max_src_len"]), int(host_batches[0]["max_mel_len"])
+    line = {
+        "metric": wl["metric"], "value": all_frames / (ms_dev * 1e-3), "unit": wl["unit"], "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl_name}: base config random init, teacher-forced synthesis forward, B={B}/GPU, T<={T}, F<={F}, 80-bin mel",
+                   "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "parallelism": f"replicas x{world}, no collectives"},
+        "e2e": {"value": all_frames / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
+                "d2h_bytes_per_step": B * F * 80 * 4 + B * 4, "ms_per_step": ms_e2e / args.steps, "api": "FastSpeech2.predict_step"},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "step_flops": flops_fwd(B, T, F), "step_tflops": flops_fwd(B, T, F) / (ms_dev / args.steps * 1e-3) / 1e12,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl, cfg, host_batches[0])
+    return line
+
+
+def run_mas(args, wl_name, wl, rank, world, device, pk):
+    import numpy as np
+
+    from fastspeech2_lightning_b200 import ops
+
+    B, F, T = wl["batch"], wl["F"], wl["T"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    soft = torch.softmax(torch.randn(B, 1, F, T, generator=g) * 2, dim=-1)
+    il = torch.full((B,), T, dtype=torch.int32)
+    ol = torch.full((B,), F, dtype=torch.int32)
+    hs, hil, hol = soft.pin_memory(), il.pin_memory(), ol.pin_memory()
+    ds, dil, dol = soft.to(device), il.to(device), ol.to(device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def step(i):
+        return ops.mas(ds, dil, dol, take_log=True, dense=True)
+
+    def step_e2e(i):
+        _, dur, hard = ops.mas(hs.to(device, non_blocking=True), hil.to(device, non_blocking=True), hol.to(device, non_blocking=True), take_log=True, dense=True)
+        return dur.cpu()
+
+    for i in range(args.warmup):
+        step(i); step_e2e(i)
+
+    def timed(fn):
+        evs = []
+        torch.cuda.synchronize()
+        for i in range(args.steps):
+            flush.fill_(i & 1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(i); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    l0 = ops.launch_count
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        ms = timed(step)
+        launches = ops.launch_count - l0
+        ms_e2e = timed(step_e2e)
+    per = ms / args.steps
+    ach = 8.0 * B * F * T / (per * 1e-3) / 1e9
+    line = {"metric": wl["metric"], "value": per, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl_name}: batched MAS (log + DP + backtrack + dense map) on [B={B},1,F={F},T={T}]", "l2": "flushed between timed iterations"},
+            "e2e": {"value": ms_e2e / args.steps, "unit": wl["unit"], "h2d_bytes_per_step": B * F * T * 4 + 8 * B, "d2h_bytes_per_step": B * T * 4},
+            "gpu_launches": launches, "clocks": clk.summary(),
+            "roofline": {"kernel": "fs2k_mas_fwd", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"]}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import intops
+
+        x = torch.log(soft).numpy()
+        t0 = time.perf_counter(); intops.b_mas(x, il.numpy(), ol.numpy(), threads=1); t1 = time.perf_counter() - t0
+        reps = max(1, int(3.0 / max(t1, 1e-3)))
+        best = min(_time(lambda: intops.b_mas(x, il.numpy(), ol.numpy(), threads=1)) for _ in range(min(reps, 20)))
+        line["cpu_baseline"] = {"value": best * 1e3, "unit": wl["unit"], "cores": 1, "kind": "port", "sample": f"oracle C restatement of mas_width1, serial per-item loop as in binarize_attention, same [B={B},F={F},T={T}] batch, best of {min(reps, 20)}"}
+    return line
+
+
+def _time(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
+
+
+def cpu_forward_fn(wl, cfg, batch):
+    from oracle import fs2_oracle
+
+    _, model = build_model(wl, None)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    ocfg = fs2_oracle.Cfg(cfg)
+
+    def fn():
+        with torch.no_grad():
+            return fs2_oracle.forward(sd, ocfg, batch, inference=True)
+
+    return fn
+
+
+def cpu_baseline(wl, cfg, batch):
+    """The oracle port of the reference's CPU path on the host cores, same batch (bounded sample)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn = cpu_forward_fn(wl, cfg, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    fn()
+    best = min(_time(fn) for _ in range(3))
+    frames = int(batch["mel_lens"].sum())
+    return {"value": frames / best, "unit": wl["unit"], "cores": cores, "kind": "port",
+            "sample": f"oracle (torch-CPU restatement of the reference forward) on one batch of the workload ({frames} frames), best of 3, {best*1e3:.0f} ms"}
+
+
+def run_reference(args, wl_name, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if wl["kind"] == "mas":
+        from oracle import intops
+
+        B, F, T = wl["batch"], wl["F"], wl["T"]
+        g = torch.Generator().manual_seed(1234)
+        x = torch.log_softmax(torch.randn(B, 1, F, T, generator=g) * 2, dim=-1).numpy()
+        il, ol = [T] * B, [F] * B
+        for _ in range(args.warmup):
+            intops.b_mas(x, il, ol)
+        t = sum(_time(lambda: intops.b_mas(x, il, ol)) for _ in range(args.steps))
+        v = t / args.steps * 1e3
+        return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": v, "higher_is_better": False, "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name},
+                "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port", "sample": "oracle b_mas (OpenMP over items)"},
+                "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cfg, _ = build_model(wl, None)
+    batches = make_batches(wl, 2, 0)
+    fns = [cpu_forward_fn(wl, cfg, b) for b in batches]
+    steps = min(args.steps, 8)  # bounded sample: a CPU step takes ~0.5-2 s
+    for i in range(min(args.warmup, 2)):
+        fns[i % 2]()
+    t = sum(_time(fns[i % 2]) for i in range(steps))
+    frames = sum(int(batches[i % 2]["mel_lens"].sum()) for i in range(steps))
+    v = frames / t
+    B, T, F = wl["batch"], int(batches[0]["max_src_len"]), int(batches[0]["max_mel_len"])
+    return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 2),
+            "ms_per_step": t / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl_name}: base config random init, teacher-forced synthesis forward, B={B}, T<={T}, F<={F}, 80-bin mel"},
+            "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
+                             "sample": f"{steps} steps of the same workload on the host CPU (oracle port: the reference is pure Python and /root/reference does not travel)"},
+            "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synth_c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        line = run_reference(args, args.workload, wl, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    line = run_ours(args, args.workload, wl, rank, world, device)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

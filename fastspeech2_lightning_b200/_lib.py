@@ -58,12 +58,53 @@ def parse_header(path: Path = HEADER) -> dict[str, tuple[object, list[object]]]:
 
 
 _lib = None
+_profile_records = None  # list of (entry point, args, start event, end event) while profiling
 
 
-def lib() -> ctypes.CDLL:
+class _ProfilingProxy:
+    """Wraps every C-ABI call in a pair of CUDA events on the current stream (bench.py's roofline pass)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("fs2k_") or name in ("fs2k_strerror", "fs2k_version", "fs2k_check_device") or name.endswith("_bytes"):
+            return fn
+
+        def timed(*args):
+            import torch
+
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            _profile_records.append((name, args, s, e))
+            return rc
+
+        return timed
+
+
+def start_profile() -> None:
+    global _profile_records
+    _profile_records = []
+
+
+def stop_profile():
+    """Returns [(entry point, args, milliseconds)] of every call since start_profile()."""
+    global _profile_records
+    import torch
+
+    torch.cuda.synchronize()
+    out = [(n, a, s.elapsed_time(e)) for n, a, s, e in _profile_records]
+    _profile_records = None
+    return out
+
+
+def lib():
     global _lib
     if _lib is not None:
-        return _lib
+        return _ProfilingProxy(_lib) if _profile_records is not None else _lib
     from . import build as _build
 
     if shutil.which(_build.NVCC) or Path(_build.NVCC).exists():
