@@ -1,0 +1,439 @@
+// Tensor-core GEMM / 1-D convolution for sm_100a: TMA → shared memory → tcgen05.mma (kind::tf32,
+// accumulators in TMEM) → fused epilogue.  Same contract as fs2k_gemm_f32 (gemm_simt.cu):
+//
+//   C[(b,l), n] = (act((Σ_tap Σ_k A[b, l+tap−pad, k] · W[tap][n][k] + bias[n])·scale[n] + shift[n])·alpha
+//                 + residual[(b,l), n]) · row_mask[(b,l)]          (+ optional LayerNorm of the finished row)
+//
+// One 128 × BLOCK_N output tile per CTA (BLOCK_N = N when N ≤ 256, else 256).  Operands stay fp32 in
+// HBM: TMA brings 128-row × 32-float boxes (one 128-byte swizzle atom per row) into a 4-stage ring; the
+// convolution taps are time-shifted boxes of a 3-D tensor map [B][L][K] whose out-of-range rows TMA
+// zero-fills, so a tap never crosses an utterance boundary and no im2col buffer exists.  One elected
+// thread issues four K=8 tf32 MMAs per stage.  `passes = 3` adds the split-accumulate 3×TF32 scheme
+// (big·big + big·small + small·big, small = x − tf32(x)) that restores fp32-level accuracy.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = operand splitter helper,
+// 4-7 = TMEM → registers → staging tile in shared memory (per-column epilogue math); then all eight
+// warps store the tile with fully coalesced 16-byte accesses, adding the residual, the row mask and,
+// when requested, the LayerNorm of the row (a row lives in one warp, so mean/var are two shuffles).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fs2k {
+
+constexpr int TC_BM = 128;      // rows per tile == TMEM lanes
+constexpr int TC_BK = 32;       // fp32 elements per 128-byte swizzle atom
+template <int PASSES> struct TcStages { static constexpr int value = PASSES == 3 ? 2 : 4; };  // 3×TF32 keeps a second copy of every tile
+constexpr int TC_THREADS = 256;
+
+struct TcEpilogue {
+    const float* bias; const float* scale; const float* shift;
+    int act; float alpha;
+    const float* residual; int ldr;
+    const uint8_t* row_mask;
+    float* C; int ldc;
+    // optional fused LayerNorm of the finished row (requires BLOCK_N == N)
+    const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_out; int ld_ln;
+    const float* ln2_gamma; const float* ln2_beta; float* ln2_out;  // second LN chained on ln_out
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    if (act == FS2K_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == FS2K_ACT_SILU) return silu(v);
+    if (act == FS2K_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+// small = x − tf32(x) for every fp32 of a staged operand tile (elementwise: layout/swizzle agnostic)
+__device__ __forceinline__ void split_small(const float4* src, float4* dst, int n_vec, int tid, int nthreads) {
+    for (int i = tid; i < n_vec; i += nthreads) {
+        float4 v = src[i];
+        v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        dst[i] = v;
+    }
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, TcEpilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int TC_STAGES = TcStages<PASSES>::value;
+    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_split[TC_STAGES], s_tmem_full;
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_colp[3][256];
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = block_n * TC_BK * 4;
+    const uint32_t stage_bytes = (a_bytes + b_bytes) * (PASSES == 3 ? 2 : 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tile_m = blockIdx.x, n0 = blockIdx.y * block_n;
+    const int b_idx = tile_m / tiles_per_b, l0 = (tile_m % tiles_per_b) * TC_BM;
+    const int nk = (K + TC_BK - 1) / TC_BK;
+    const int iters = taps * nk;
+
+    // per-column epilogue parameters → shared memory
+    for (int c = threadIdx.x; c < block_n; c += TC_THREADS) {
+        s_colp[0][c] = ep.bias ? ep.bias[n0 + c] : 0.f;
+        s_colp[1][c] = ep.scale ? ep.scale[n0 + c] : 1.f;
+        s_colp[2][c] = ep.scale ? ep.shift[n0 + c] : 0.f;
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&s_empty[s]), 1);
+            mbar_init(smem_u32(&s_split[s]), 32);
+        }
+        mbar_init(smem_u32(&s_tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        // 256 accumulator columns cover every BLOCK_N ≤ 256 (power of two ≥ 32 required)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&s_tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+                const int tap = it / nk, k0 = (it - tap * nk) * TC_BK;
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+                const uint32_t bar = smem_u32(&s_full[s]);
+                mbar_expect_tx(bar, a_bytes + b_bytes);
+                tma_load_3d(sa, &tmA, bar, k0, l0 + tap - pad, b_idx);
+                tma_load_2d(sb, &tmB, bar, k0, tap * N + n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = make_idesc_tf32(block_n);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait(smem_u32(PASSES == 3 ? &s_split[s] : &s_full[s]), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t ad = make_smem_desc(sa + k * 32), bd = make_smem_desc(sb + k * 32);
+                    tc_mma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+                    if (PASSES == 3) {
+                        const uint64_t ads = make_smem_desc(sa + a_bytes + b_bytes + k * 32);
+                        const uint64_t bds = make_smem_desc(sb + a_bytes + b_bytes + k * 32);
+                        tc_mma_tf32(tmem_base, ad, bds, idesc, 1u);
+                        tc_mma_tf32(tmem_base, ads, bd, idesc, 1u);
+                    }
+                }
+                tc_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs have read it
+            }
+            tc_commit(smem_u32(&s_tmem_full));
+        }
+    } else if (warp == 3) {
+        if (PASSES == 3) {
+            // ================= operand splitter (3×TF32): small parts of A and W next to the originals ==========
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&s_full[s]), ph);
+                const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+                float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes + b_bytes);
+                split_small(src, dst, (a_bytes + b_bytes) / 16, lane, 32);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes → visible to the MMA proxy
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_split[s])) : "memory");
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue stage 1: TMEM → registers → per-column math → staging tile =================
+        mbar_wait(smem_u32(&s_tmem_full), 0);
+        tc_fence_after();
+        const int q = warp & 3;              // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        const int pitch = block_n + 4;
+        float* stag = reinterpret_cast<float*>(smem);
+        for (int c0 = 0; c0 < block_n; c0 += 16) {
+            float v[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = v[j] + s_colp[0][c0 + j];
+                x = x * s_colp[1][c0 + j] + s_colp[2][c0 + j];
+                v[j] = tc_act(x, ep.act) * ep.alpha;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(stag + (size_t)row * pitch + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+
+    // ================= epilogue stage 2: coalesced stores (+ residual, row mask, LayerNorm) =================
+    {
+        const int pitch = block_n + 4;
+        const float* stag = reinterpret_cast<const float*>(smem);
+        const int nv = block_n >> 2;  // float4 per row (≤ 64)
+        const bool do_ln = ep.ln_out != nullptr;
+        for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
+            const int l = l0 + r;
+            if (l >= L) break;
+            const long m = (long)b_idx * L + l;
+            if (m >= M_total) break;
+            const float rm = ep.row_mask ? (ep.row_mask[m] ? 1.f : 0.f) : 1.f;
+            float4 val[2];
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int qv = lane + 32 * j;
+                if (qv < nv) {
+                    float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
+                    if (ep.residual) {
+                        const float4 rr = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n0 + qv * 4);
+                        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                    }
+                    if (ep.row_mask) { v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm; }
+                    if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
+                    val[j] = v;
+                    sum += (v.x + v.y) + (v.z + v.w);
+                } else {
+                    val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (do_ln) {
+                // LayerNorm over the N = block_n columns of this row (held by this warp)
+                const float inv_n = 1.0f / (float)block_n;
+                float mean = warp_sum(sum) * inv_n;
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (lane + 32 * j < nv) {
+                        const float a = val[j].x - mean, b = val[j].y - mean, c = val[j].z - mean, d = val[j].w - mean;
+                        ss += (a * a + b * b) + (c * c + d * d);
+                    }
+                float rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
+                float sum2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int qv = lane + 32 * j;
+                    if (qv < nv) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + qv);
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + qv);
+                        float4 o;
+                        o.x = (val[j].x - mean) * rstd * g.x + bb.x;
+                        o.y = (val[j].y - mean) * rstd * g.y + bb.y;
+                        o.z = (val[j].z - mean) * rstd * g.z + bb.z;
+                        o.w = (val[j].w - mean) * rstd * g.w + bb.w;
+                        *reinterpret_cast<float4*>(ep.ln_out + (size_t)m * ep.ld_ln + qv * 4) = o;
+                        val[j] = o;
+                        sum2 += (o.x + o.y) + (o.z + o.w);
+                    }
+                }
+                if (ep.ln2_out) {  // second LayerNorm chained on the first one's output
+                    mean = warp_sum(sum2) * inv_n;
+                    ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (lane + 32 * j < nv) {
+                            const float a = val[j].x - mean, b = val[j].y - mean, c = val[j].z - mean, d = val[j].w - mean;
+                            ss += (a * a + b * b) + (c * c + d * d);
+                        }
+                    rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int qv = lane + 32 * j;
+                        if (qv < nv) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma) + qv);
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln2_beta) + qv);
+                            float4 o;
+                            o.x = (val[j].x - mean) * rstd * g.x + bb.x;
+                            o.y = (val[j].y - mean) * rstd * g.y + bb.y;
+                            o.z = (val[j].z - mean) * rstd * g.z + bb.z;
+                            o.w = (val[j].w - mean) * rstd * g.w + bb.w;
+                            *reinterpret_cast<float4*>(ep.ln2_out + (size_t)m * ep.ld_ln + qv * 4) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+}  // namespace fs2k
+
+using namespace fs2k;
+
+extern "C" int fs2k_gemm_tc_supported(int K, int N, int lda, int taps) {
+    if (K <= 0 || N <= 0 || taps < 1) return 0;
+    if ((lda & 3) || (K & 3)) return 0;                     // TMA: 16-byte global strides
+    if (N <= 256) return (N % 16) == 0;
+    return (N % 256) == 0 || (N % 128) == 0;
+}
+
+extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
+                            const float* bias, const float* scale, const float* shift, int act, float alpha,
+                            const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
+                            const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
+                            const float* ln2_gamma, const float* ln2_beta, float* ln2_out, int passes,
+                            fs2k_stream_t stream) {
+    FS2K_REQUIRE(B >= 0 && L >= 0 && K > 0 && N > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
+    FS2K_REQUIRE(act >= 0 && act <= 3 && (passes == 1 || passes == 3), FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(fs2k_gemm_tc_supported(K, N, lda, taps), FS2K_ERR_UNSUPPORTED);
+    const long M = (long)B * L;
+    if (M == 0) return FS2K_OK;
+    FS2K_REQUIRE(A && W && (C || ln_out), FS2K_ERR_NULL);
+    FS2K_REQUIRE(!scale || shift, FS2K_ERR_NULL);
+    FS2K_REQUIRE((ldc & 3) == 0 && (!residual || (ldr & 3) == 0), FS2K_ERR_UNSUPPORTED);
+    const int block_n = N <= 256 ? N : ((N % 256) == 0 ? 256 : 128);
+    FS2K_REQUIRE(!ln_out || (block_n == N && ln_gamma && ln_beta), FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(!ln2_out || (ln_out && ln2_gamma && ln2_beta), FS2K_ERR_UNSUPPORTED);
+    EncodeTiledFn encode = get_encode();
+    FS2K_REQUIRE(encode != nullptr, FS2K_ERR_ARCH);
+
+    // taps == 1: flatten to one "utterance" of M rows so tiles pack densely; otherwise tiles stay inside one b
+    const int Bm = taps == 1 ? 1 : B;
+    const long Lm = taps == 1 ? M : L;
+    FS2K_REQUIRE(Lm < (1L << 31), FS2K_ERR_UNSUPPORTED);
+    const int tiles_per_b = (int)((Lm + TC_BM - 1) / TC_BM);
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Lm, (cuuint64_t)Bm};
+        cuuint64_t strides[2] = {(cuuint64_t)lda * 4, (cuuint64_t)Lm * lda * 4};
+        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)A, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)taps * N};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
+    }
+    TcEpilogue ep{bias, scale, shift, act, alpha, residual, ldr, row_mask, C, ldc,
+                  ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out};
+    const size_t stage = (size_t)(TC_BM + block_n) * TC_BK * 4 * (passes == 3 ? 2 : 1);
+    size_t smem = stage * (passes == 3 ? TcStages<3>::value : TcStages<1>::value);
+    const size_t staging = (size_t)TC_BM * (block_n + 4) * 4;
+    if (smem < staging) smem = staging;
+    smem += 1024;  // manual 1024-byte alignment of the swizzled tiles
+    FS2K_REQUIRE(smem <= 227 * 1024, FS2K_ERR_UNSUPPORTED);
+    dim3 grid(Bm * tiles_per_b, N / block_n);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (passes == 3) {
+        e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+        gemm_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, ep);
+    } else {
+        e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+        gemm_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, ep);
+    }
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}

@@ -152,7 +152,10 @@ class FastSpeech2(_Base):
             control.duration = batch["duration_control"][0]
         teacher_forcing = bool(inference and batch["mel_lens"] is not None)
         src_lens = batch["src_lens"]
-        max_src_len = int(batch["max_src_len"])
+        msl = batch["max_src_len"]
+        # a CUDA 0-d tensor would cost a host sync per call; the padded input width is the same number
+        max_src_len = (batch["pfs"] if batch.get("text") is None else batch["text"]).shape[1] if (
+            torch.is_tensor(msl) and msl.is_cuda) else int(msl)
         mel_lens = batch["mel_lens"]
         max_mel_len = batch["max_mel_len"]
         inv_freq = self.position_embedding.inv_freq
@@ -257,7 +260,20 @@ class FastSpeech2(_Base):
         checkpoint["model_info"] = {"name": self.__class__.__name__, "version": self._VERSION}
 
     # ------------------------------------------------------------------------------------------
+    def enable_cuda_graphs(self, enabled: bool = True):
+        """Replay teacher-forced synthesis (`predict_step` on batches that carry `mel_lens`) from CUDA graphs,
+        one graph per (B, T, F) shape.  Turns the Σduration host check off (graphs cannot read back)."""
+        from ..graphs import GraphedSynthesis
+
+        self._graphed = GraphedSynthesis(self) if enabled else None
+        if enabled and self.variance_adaptor is not None:
+            self.variance_adaptor.validate_durations = False
+        return self
+
     def predict_step(self, batch, batch_idx):
+        graphed = getattr(self, "_graphed", None)
+        if graphed is not None and batch.get("mel_lens") is not None and not self.training:
+            return graphed(batch)
         with torch.no_grad():
             return self(batch, inference=True)
 

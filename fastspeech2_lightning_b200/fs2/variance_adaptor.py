@@ -190,8 +190,18 @@ class VarianceAdaptor(nn.Module):
         else:  # :359-366
             duration_rounded = ops.round_durations(log_duration_prediction.detach(), control.duration)
         frame_level = "frame" in (cfgm.variance_predictors.energy.level.value, cfgm.variance_predictors.pitch.level.value)
+        # With given durations (training / teacher forcing) Σdur == mel_lens, so the output width is the
+        # batch's max_mel_len and no host read is needed; free-running synthesis reads the totals once.
+        known_width = None
+        if (teacher_forcing or not inference) and not self.validate_durations:
+            mml = batch["max_mel_len"]
+            if torch.is_tensor(mml) and mml.is_cuda:
+                known_width = batch["mel"].shape[1] if batch.get("mel") is not None else int(mml)
+            else:
+                known_width = int(mml)
         x, x_pos, tgt_mask, scan = self.length_regulator.expand(
-            x, duration_rounded, max_length=max_target_len, inv_freq=None if frame_level else inv_freq)
+            x, duration_rounded, max_length=max_target_len, inv_freq=None if frame_level else inv_freq,
+            known_width=known_width)
 
         if cfgm.variance_predictors.energy.level.value == "frame":  # :371-383
             energy_prediction, x, _ = self._variance_embed_add(

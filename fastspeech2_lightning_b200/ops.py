@@ -270,8 +270,83 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# Arithmetic of the dense contractions:
+#   "fp32"   exact FFMA kernel (gemm_simt.cu)
+#   "tf32x3" tcgen05 tensor cores, 3×TF32 split accumulation — fp32-level accuracy (default)
+#   "tf32"   tcgen05 tensor cores, single TF32 pass
+PRECISION = "tf32x3"
+
+
+def set_precision(mode: str) -> None:
+    global PRECISION
+    if mode not in ("fp32", "tf32", "tf32x3"):
+        raise ValueError(mode)
+    PRECISION = mode
+
+
 def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,
-         residual=None, row_mask=None, out=None):
+         residual=None, row_mask=None, out=None, ln=None, ln2=None, want_c: bool = True):
+    """a [B,L,K] (or [M,K]) · w [taps,N,K] or [N,K] with the fused epilogue of fs2k_gemm_{tc,f32}.
+
+    ln = (gamma, beta, eps): also return LayerNorm(result) — fused into the tensor-core epilogue when one
+    tile spans the row, otherwise a separate fs2k_layernorm_fwd launch; ln2 = (gamma, beta) chains a second
+    LayerNorm on the first one's output.  Returns C, or (C, ln_out[, ln2_out]) when ln is given."""
+    if ln is not None or PRECISION != "fp32":
+        r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c)
+        if r is not None:
+            return r
+    c = _gemm_f32(a, w, bias, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha, residual=residual,
+                  row_mask=row_mask, out=out)
+    if ln is None:
+        return c
+    y = layernorm(c, ln[0], ln[1], ln[2])
+    if ln2 is None:
+        return c, y
+    return c, y, layernorm(y, ln2[0], ln2[1], ln[2])
+
+
+def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c):
+    if PRECISION == "fp32":
+        return None
+    a = _f32(a, "a")
+    if a.dim() == 2:
+        B, L, K = 1, a.shape[0], a.shape[1]
+        out_shape = (L,)
+    else:
+        B, L, K = a.shape
+        out_shape = (B, L)
+    w = _f32(w, "w")
+    if w.dim() == 2:
+        w = w.reshape(1, *w.shape)
+    taps, N, Kw = w.shape
+    assert Kw == K, (Kw, K)
+    if not lib().fs2k_gemm_tc_supported(K, N, K, taps) or (a.data_ptr() & 15) or (w.data_ptr() & 15):
+        return None
+    fuse_ln = ln is not None and N <= 256
+    dev = a.device
+    c = out if out is not None else (torch.empty((*out_shape, N), dtype=torch.float32, device=dev) if (want_c or not fuse_ln) else None)
+    if residual is not None:
+        residual = _f32(residual, "residual")
+    if row_mask is not None:
+        row_mask = row_mask.contiguous()
+    ln_out = torch.empty((*out_shape, N), dtype=torch.float32, device=dev) if fuse_ln else None
+    ln2_out = torch.empty((*out_shape, N), dtype=torch.float32, device=dev) if (fuse_ln and ln2 is not None) else None
+    check(lib().fs2k_gemm_tc(_p(a), K, B, L, K, _p(w), N, taps, taps_pad, _p(bias), _p(scale), _p(shift), _ACTS[act],
+                             float(alpha), _p(residual), N, _p(row_mask), _p(c), N,
+                             _p(ln[0]) if fuse_ln else None, _p(ln[1]) if fuse_ln else None, float(ln[2]) if fuse_ln else 0.0,
+                             _p(ln_out), _p(ln2[0]) if ln2_out is not None else None, _p(ln2[1]) if ln2_out is not None else None,
+                             _p(ln2_out), 3 if PRECISION == "tf32x3" else 1, _stream()), "fs2k_gemm_tc")
+    _count()
+    if ln is None:
+        return c
+    if not fuse_ln:
+        y = layernorm(c, ln[0], ln[1], ln[2])
+        return (c, y) if ln2 is None else (c, y, layernorm(y, ln2[0], ln2[1], ln[2]))
+    return (c, ln_out) if ln2 is None else (c, ln_out, ln2_out)
+
+
+def _gemm_f32(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,
+              residual=None, row_mask=None, out=None):
     """a [B,L,K] (or [M,K]) · w [taps,N,K] or [N,K] with the fused epilogue of fs2k_gemm_f32."""
     a = _f32(a, "a")
     if a.dim() == 2:

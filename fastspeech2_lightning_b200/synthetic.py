@@ -169,7 +169,8 @@ def make_batch(
 def batch_to(batch: dict, device, non_blocking: bool = False) -> dict:
     out = {}
     for k, v in batch.items():
-        out[k] = v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v
+        # 0-d shape scalars (max_src_len / max_mel_len) stay on the host: the model only reads them as ints
+        out[k] = v.to(device, non_blocking=non_blocking) if (torch.is_tensor(v) and v.dim() > 0) else v
     return out
 
 

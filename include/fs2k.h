@@ -40,6 +40,8 @@ enum { FS2K_ACT_NONE = 0, FS2K_ACT_RELU = 1, FS2K_ACT_SILU = 2, FS2K_ACT_TANH = 
 const char* fs2k_strerror(int code);
 int fs2k_version(void);
 int fs2k_check_device(void); /* FS2K_OK iff the current device is compute capability 10.x */
+/* keeps `stream` busy for ns nanoseconds (measurement aid: lets the host queue work ahead of the GPU) */
+int fs2k_spin_ns(long ns, fs2k_stream_t stream);
 
 /* ---- monotonic alignment search -------------------------------------------------------------
  * replaces VarianceAdaptor.binarize_attention (fs2/variance_adaptor.py:160-181) and
@@ -119,6 +121,18 @@ int fs2k_affine_act(const float* z, const float* scale, const float* shift, int 
 int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
                   const float* bias, const float* scale, const float* shift, int act, float alpha,
                   const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, fs2k_stream_t stream);
+/* Tensor-core path (tcgen05.mma kind::tf32, TMEM accumulators, TMA operand boxes; gemm_tc.cu): same
+ * contract as fs2k_gemm_f32; passes = 1 (single TF32) or 3 (3xTF32 split accumulation, fp32-level accuracy).
+ * Optional fused LayerNorm(s) of the finished row when one tile spans the row (N <= 256):
+ * ln_out = LN(C; ln_gamma, ln_beta), ln2_out = LN(ln_out; ln2_gamma, ln2_beta); C may be NULL if only
+ * the normalised row is wanted.  fs2k_gemm_tc_supported: K % 4 == 0, lda % 4 == 0, N % 16 == 0 (N <= 256)
+ * or N % 128 == 0. */
+int fs2k_gemm_tc_supported(int K, int N, int lda, int taps);
+int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
+                 const float* bias, const float* scale, const float* shift, int act, float alpha,
+                 const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, const float* ln_gamma,
+                 const float* ln_beta, float ln_eps, float* ln_out, const float* ln2_gamma, const float* ln2_beta,
+                 float* ln2_out, int passes, fs2k_stream_t stream);
 int fs2k_rowdot(const float* x, const float* w, const float* b, const uint8_t* mask, long M, int D, float* y,
                 fs2k_stream_t stream);
 int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);

@@ -248,7 +248,7 @@ def test_gemm_conv_epilogues(B, L, K, N, taps, act, extra):
         ref = ref * rm[..., None]
         kw.update(row_mask=rm.to(dev()))
     wt = o.conv_weight_taps(w.to(dev()))
-    got = o.gemm(x.to(dev()), wt, None if bias is None else bias.to(dev()), taps_pad=(taps - 1) // 2, act=act, **kw)
+    got = o._gemm_f32(x.to(dev()), wt, None if bias is None else bias.to(dev()), taps_pad=(taps - 1) // 2, act=act, **kw)
     close(got, ref, 2e-5, f"gemm {B}x{L}x{K}->{N} taps{taps} {act} {extra}")
 
 
@@ -354,3 +354,66 @@ def test_losses():
     ref = -torch.log(torch.clamp(soft[hard == 1], min=1e-12)).sum() / hard.sum()
     loss, _ = o.bin_loss_fwd(hard.to(dev()), soft.to(dev()), 1e-12)
     close(loss, ref, 1e-5, "bin loss")
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 tensor-core GEMM (TMA + TMEM): same contract as the FFMA kernel
+# ------------------------------------------------------------------------------------------------
+TC_CASES = [
+    (2, 100, 256, 1024, 1, "silu", ""), (16, 80, 1024, 256, 1, None, "res_alpha"), (3, 77, 256, 768, 1, None, ""),
+    (2, 130, 80, 512, 5, "tanh", "bn"), (2, 130, 512, 80, 5, None, "bn_res"), (4, 33, 256, 512, 3, "relu", ""),
+    (2, 64, 160, 80, 1, "relu", ""), (2, 9, 512, 512, 5, "tanh", "bn"), (1, 1, 256, 80, 1, None, ""),
+    (3, 50, 256, 256, 3, "relu", "mask"), (5, 300, 256, 256, 1, None, "res_ln"), (2, 140, 1024, 256, 1, None, "res_alpha_ln2"),
+    (1, 3000, 256, 256, 1, "relu", "ln"),
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 6e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("B,L,K,N,taps,act,extra", TC_CASES)
+def test_gemm_tensor_core(mode, tol, B, L, K, N, taps, act, extra):
+    o = ops()
+    g = torch.Generator().manual_seed(B * 1000 + L + N)
+    x = torch.randn(B, L, K, generator=g)
+    w = torch.randn(N, K, taps, generator=g) / (K * taps) ** 0.5
+    bias = torch.randn(N, generator=g) * 0.1
+    ref = F.conv1d(x.transpose(1, 2), w, bias, padding=(taps - 1) // 2).transpose(1, 2)
+    kw = {}
+    if "bn" in extra:
+        sc, sh = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+        ref = ref * sc + sh
+        kw.update(scale=sc.to(dev()), shift=sh.to(dev()))
+    if act:
+        ref = {"silu": F.silu, "relu": F.relu, "tanh": torch.tanh}[act](ref)
+    if "res" in extra:
+        res = torch.randn(B, L, N, generator=g)
+        alpha = 0.5 if "alpha" in extra else 1.0
+        ref = ref * alpha + res
+        kw.update(residual=res.to(dev()), alpha=alpha)
+    if "mask" in extra:
+        rm = torch.rand(B, L, generator=g) > 0.3
+        ref = ref * rm[..., None]
+        kw.update(row_mask=rm.to(dev()))
+    ln_ref = ln2_ref = None
+    if "ln" in extra:
+        g1, b1 = torch.randn(N, generator=g), torch.randn(N, generator=g)
+        ln_ref = F.layer_norm(ref, (N,), g1, b1, 1e-5)
+        kw.update(ln=(g1.to(dev()), b1.to(dev()), 1e-5))
+        if "ln2" in extra:
+            g2, b2 = torch.randn(N, generator=g), torch.randn(N, generator=g)
+            ln2_ref = F.layer_norm(ln_ref, (N,), g2, b2, 1e-5)
+            kw.update(ln2=(g2.to(dev()), b2.to(dev())))
+    wt = o.conv_weight_taps(w.to(dev()))
+    prev = o.PRECISION
+    o.set_precision(mode)
+    try:
+        got = o.gemm(x.to(dev()), wt, bias.to(dev()), taps_pad=(taps - 1) // 2, act=act, **kw)
+    finally:
+        o.set_precision(prev)
+    what = f"gemm_tc[{mode}] {B}x{L}x{K}->{N} taps{taps} {act} {extra}"
+    if ln_ref is None:
+        close(got, ref, tol, what)
+    else:
+        close(got[0], ref, tol, what)
+        close(got[1], ln_ref, tol * 5, what + " ln")
+        if ln2_ref is not None:
+            close(got[2], ln2_ref, tol * 5, what + " ln2")
