@@ -29,6 +29,8 @@ WORKLOADS = {
     "synth_c1": dict(kind="synth", batch=16, src=(60, 80), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
     # configs[3]: 256 utterances of 20-200 phonemes in length-sorted batches of 32 (one step = one batch of 32)
     "synth_c4": dict(kind="synth", batch=32, src=(20, 200), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
+    # configs[1] (N=1, fp32) / configs[2] (N>1): training step with learned alignment, batch 32 per GPU
+    "train_c2": dict(kind="train", batch=32, src=(60, 80), metric="train_utts_per_sec", unit="utterances/s"),
     "mas_c2": dict(kind="mas", batch=32, F=500, T=80, metric="mas_ms_per_batch", unit="ms/batch"),
     "mas_c5": dict(kind="mas", batch=1, F=8000, T=1000, metric="mas_ms_per_batch", unit="ms/batch"),
 }
@@ -156,6 +158,8 @@ def run_ours(args, wl_name, wl, rank, world, device):
     n_distinct = 4
     if wl["kind"] == "mas":
         return run_mas(args, wl_name, wl, rank, world, device, pk)
+    if wl["kind"] == "train":
+        return run_train(args, wl_name, wl, rank, world, device, pk)
     cfg, model = build_model(wl, device)
     host_batches = [pin(b) for b in make_batches(wl, n_distinct, rank)]
     dev_batches = [synthetic.batch_to(b, device) for b in host_batches]
@@ -260,6 +264,166 @@ def run_ours(args, wl_name, wl, rank, world, device):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, cfg, host_batches[0])
     return line
+
+
+def build_train_model(device, seed=1234):
+    from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.fs2.config import FastSpeech2Config
+    from fastspeech2_lightning_b200.fs2.model import FastSpeech2
+
+    cfg = FastSpeech2Config()  # base config: learned alignment, dropout 0.2 / 0.5, AdamW + Noam
+    torch.manual_seed(seed)
+    model = FastSpeech2(cfg, stats=synthetic.DEFAULT_STATS)
+    model.train()
+    if device is not None:
+        model = model.to(device)
+        model.variance_adaptor.validate_durations = False
+        model.fused_grad_clip = 1.0  # gradient_clip_val of fs2/cli/train.py:38, fused into the optimizer launch
+    return cfg, model
+
+
+def make_train_batches(wl, n, rank):
+    from fastspeech2_lightning_b200 import synthetic
+
+    return [synthetic.make_batch(wl["batch"], wl["src"], seed=4321 + 1000 * rank + i, learn_alignment=True) for i in range(n)]
+
+
+def run_train(args, wl_name, wl, rank, world, device, pk):
+    """BASELINE configs[1]/[2]: one optimisation step = forward (aligner + MAS + both Conformers + PostNet) + losses
+    + backward + gradient clip + AdamW (+ NCCL all-reduce of the flat gradient when world > 1)."""
+    from fastspeech2_lightning_b200 import _lib, ops, synthetic
+
+    cfg, model = build_train_model(device)
+    (opt,), (sched,) = model.configure_optimizers()
+    n_distinct = 4
+    host_batches = [pin(b) for b in make_train_batches(wl, n_distinct, rank)]
+    dev_batches = [synthetic.batch_to(b, device) for b in host_batches]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def step(i):
+        batch = dev_batches[i % n_distinct]
+        opt.zero_grad()
+        out = model(batch)
+        losses = model.loss(out, batch, model.current_epoch)
+        losses["total"].backward()
+        opt.step()
+        sched["scheduler"].step()
+        return losses["total"]
+
+    def step_e2e(i):
+        batch = synthetic.batch_to(host_batches[i % n_distinct], device, non_blocking=True)
+        opt.zero_grad()
+        loss = model.training_step(batch, i)  # the reference-facing call; logs every loss with .item() (D2H reads)
+        loss.backward()
+        opt.step()
+        sched["scheduler"].step()
+        return float(loss)
+
+    l0 = ops.launch_count
+    step(0)
+    launches_per_step = ops.launch_count - l0
+    for i in range(args.warmup):
+        step(i)
+        step_e2e(i)
+    torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.fill_(i & 1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        ms_dev = timed(step, args.steps)
+        ms_e2e = timed(step_e2e, args.steps)
+
+    _lib.lib().fs2k_spin_ns(int(150e6), torch.cuda.current_stream().cuda_stream)
+    _lib.start_profile()
+    step(0)
+    recs = _lib.stop_profile()
+    by = {}
+    for name, a, ms in recs:
+        f, b = kernel_work(name, a)
+        d = by.setdefault(name, [0.0, 0.0, 0.0, 0])
+        d[0] += ms; d[1] += f; d[2] += b; d[3] += 1
+    tot_ms = sum(d[0] for d in by.values())
+    dom = max(by, key=lambda k: by[k][0])
+    d = by[dom]
+    if d[1] > 0:
+        roof = {"kernel": dom, "bound": "tensor", "achieved": d[1] / (d[0] * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=pk["source"], share_of_step=d[0] / tot_ms,
+                launches=d[3], shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]})
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    B, T, F = wl["batch"], int(host_batches[0]["max_src_len"]), int(host_batches[0]["max_mel_len"])
+    utts = B * args.steps * world
+    step_flops = 3 * flops_fwd(B, T, F, aligner=True)
+    line = {
+        "metric": wl["metric"], "value": utts / (ms_dev * 1e-3), "unit": wl["unit"], "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor cores)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"{wl_name}: base config random init, training step with learned alignment (aligner+MAS, "
+                               f"duration/pitch/energy/mel/postnet/CTC/bin losses, backward, clip 1.0, AdamW+Noam), B={B}/GPU, T<={T}, F<={F}",
+                   "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}: per-rank replicas, one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "dp1",
+                   "launch": "eager (one launch per kernel)"},
+        "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
+                "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e / args.steps, "api": "FastSpeech2.training_step + FusedAdamW.step"},
+        "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roof,
+        "step_flops": step_flops, "step_tflops": step_flops / (ms_dev / args.steps * 1e-3) / 1e12,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, secs, cores = cpu_train_baseline(wl, steps=1)
+        line["cpu_baseline"] = {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
+                                "sample": f"oracle port (torch-CPU restatement, no dropout RNG) of one full training step on one batch of the workload: {secs:.1f} s"}
+    return line
+
+
+def cpu_train_baseline(wl, steps=1):
+    """The reference's CPU training step (oracle port): forward + losses + backward + clip_grad_norm_(1.0) + AdamW."""
+    from oracle import fs2_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, model = build_train_model(None)
+    ocfg = fs2_oracle.Cfg(cfg)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "_bins", "inv_freq")):
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6)
+    batches = make_train_batches(wl, 2, 0)
+
+    def one(i):
+        opt.zero_grad()
+        out = fs2_oracle.forward(sd, ocfg, batches[i % 2], training=True, new_stats={})
+        losses = fs2_oracle.loss(out, batches[i % 2], ocfg, 0)
+        losses["total"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+
+    one(0)  # warm-up
+    t = sum(_time(lambda: one(i + 1)) for i in range(steps))
+    return wl["batch"] * steps / t, t / steps, cores
 
 
 def run_mas(args, wl_name, wl, rank, world, device, pk):
@@ -373,6 +537,15 @@ def run_reference(args, wl_name, wl, rank, world):
         return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": v, "higher_is_better": False, "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name},
                 "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port", "sample": "oracle b_mas (OpenMP over items)"},
+                "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if wl["kind"] == "train":
+        steps = min(args.steps, 2)  # a CPU training step takes several seconds
+        v, secs, cores = cpu_train_baseline(wl, steps=steps)
+        return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": steps, "warmup": 1,
+                "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{wl_name}: base config random init, training step with learned alignment, B={wl['batch']}"},
+                "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
+                                 "sample": f"{steps} training steps of the same workload on the host CPU (oracle port; dropout RNG not included)"},
                 "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     cfg, _ = build_model(wl, None)
     batches = make_batches(wl, 2, 0)

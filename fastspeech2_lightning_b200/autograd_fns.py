@@ -1,162 +1,492 @@
-"""`torch.autograd.Function`s over libfs2k kernels (forward AND backward are kernel launches).
-
-`autograd.py` routes here whenever a gradient is required; ops without trainable inputs are plain
-forwards.  Backward kernels live in csrc/*_bwd.cu (built in the training milestone); until an op's
-backward exists its Function raises in `backward`, never silently falls back to torch math.
+"""`torch.autograd.Function`s over libfs2k kernels: forward AND backward are kernel launches;
+torch.autograd only sequences them.  `autograd.py` routes here whenever a gradient is required.
 """
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import ops
 
-DROPOUT_IMPLEMENTED = False
+DROPOUT_IMPLEMENTED = True
 
 
-def _grad_on(*ts) -> bool:
-    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in ts)
-
-
-class _Pending(torch.autograd.Function):
-    """Marks an output as depending on its inputs; raises if a backward is actually requested."""
-
-    @staticmethod
-    def forward(ctx, name, out, *inputs):
-        ctx.name = name
-        return out.view_as(out)
-
-    @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError(f"backward kernel for '{ctx.name}' is not built yet")
-
-
-def _pending(name, out, *inputs):
-    if _grad_on(*inputs):
-        if isinstance(out, tuple):
-            return tuple(_Pending.apply(name, o, *inputs) if o is not None and o.is_floating_point() else o for o in out)
-        return _Pending.apply(name, out, *inputs)
-    return out
+def _d(t):
+    return None if t is None else t.detach()
 
 
 # ---------------------------------------------------------------------------------------------
-def layernorm(x, weight, bias, eps, dropout=0.0):
-    assert not dropout, "dropout kernels pending"
-    return _pending("layernorm", ops.layernorm(x, weight.detach(), bias.detach(), eps), x, weight, bias)
+# dropout (Philox-free counter hash: the mask is regenerated from (seed, offset) in backward)
+# ---------------------------------------------------------------------------------------------
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        seed = int(torch.randint(0, 2**31 - 1, (1,)).item())
+        ctx.seed, ctx.p = seed, p
+        return ops.dropout(x, p, seed)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return ops.dropout(g.contiguous(), ctx.p, ctx.seed), None
 
 
-def linear(x, weight, bias, act, alpha, residual, dropout=0.0):
-    assert not dropout, "dropout kernels pending"
-    y = ops.gemm(x.detach(), weight.detach(), None if bias is None else bias.detach(), act=act, alpha=alpha,
-                 residual=None if residual is None else residual.detach())
-    return _pending("linear", y, x, weight, bias, residual)
+def dropout(x, p: float):
+    if not p:
+        return x
+    return _Dropout.apply(x, float(p))
+
+
+# ---------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight)
+        return dx, dw, db, None
+
+
+def layernorm(x, weight, bias, eps, dropout_p=0.0):
+    return dropout(_LayerNorm.apply(x.contiguous(), weight, bias, eps), dropout_p)
+
+
+# ---------------------------------------------------------------------------------------------
+def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b):
+    """Shared by every contraction: g = gradient w.r.t. the pre-activation conv output."""
+    taps, N, K = w_taps.shape
+    dx = dw = db = None
+    if needs_b:
+        db = ops.colsum(g)
+    if needs_x:
+        dx = ops.gemm(g, ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
+    if needs_w:
+        dw = ops.gemm_wgrad(g, x, taps, pad, conv_layout)
+    return dx, dw, db
+
+
+class _Gemm(torch.autograd.Function):
+    """y = act(conv(x, W) + b)·alpha + residual   (Linear when W is 2-D)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, alpha):
+        conv_layout = weight.dim() == 3
+        w_taps = ops.conv_weight_taps(weight) if conv_layout else weight.reshape(1, *weight.shape)
+        pad = (w_taps.shape[0] - 1) // 2
+        aux = None
+        if act == "silu":  # keep the pre-activation for silu'
+            aux = ops.gemm(x, w_taps, bias, taps_pad=pad)
+            y = ops.affine_act(aux, None, None, "silu", residual)
+            if alpha != 1.0:
+                raise NotImplementedError("alpha with silu")
+        else:
+            y = ops.gemm(x, w_taps, bias, taps_pad=pad, act=act, alpha=alpha, residual=residual)
+            if act in ("relu", "tanh"):
+                if residual is not None or alpha != 1.0:
+                    raise NotImplementedError("relu/tanh epilogue with residual/alpha in training")
+                aux = y
+        ctx.save_for_backward(x, w_taps, aux)
+        ctx.meta = (act, alpha, pad, conv_layout, bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w_taps, aux = ctx.saved_tensors
+        act, alpha, pad, conv_layout, has_bias, has_res = ctx.meta
+        g = g.contiguous()
+        gz = g if (act is None and alpha == 1.0) else ops.act_bwd(g, aux, act, alpha)
+        dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None
+
+
+def linear(x, weight, bias, act, alpha, residual, dropout_p=0.0):
+    if residual is not None and dropout_p:
+        # reference order: residual + Dropout(Linear(...)·alpha)
+        y = _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha)
+        return add(dropout(y, dropout_p), residual)
+    return dropout(_Gemm.apply(x.contiguous(), weight, bias, residual, act, alpha), dropout_p)
 
 
 def conv1d(x, weight, bias, act):
-    w = ops.conv_weight_taps(weight)
-    y = ops.gemm(x.detach(), w, None if bias is None else bias.detach(), taps_pad=(weight.shape[-1] - 1) // 2, act=act)
-    return _pending("conv1d", y, x, weight, bias)
+    return _Gemm.apply(x.contiguous(), weight, bias, None, act, 1.0)
 
 
-def conv1d_bn_act(x, weight, bias, bn, act, training, dropout=0.0):
-    assert not dropout, "dropout kernels pending"
-    w = ops.conv_weight_taps(weight)
-    pad = (weight.shape[-1] - 1) // 2
-    xd, bd = x.detach(), None if bias is None else bias.detach()
-    if not training:
-        scale, shift = ops.bn_scale_shift(bn, None, False)
-        y = ops.gemm(xd, w, bd, taps_pad=pad, scale=scale, shift=shift, act=act)
-    else:
-        z = ops.gemm(xd, w, bd, taps_pad=pad)
-        scale, shift = ops.bn_scale_shift(bn, z, True)
+# ---------------------------------------------------------------------------------------------
+class _ConvBnAct(torch.autograd.Function):
+    """One PostNet block: Conv1d(k) → BatchNorm1d → act (fs2/layers.py:157-212)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn_w, bn_b, bn, act, training):
+        w_taps = ops.conv_weight_taps(weight)
+        pad = (w_taps.shape[0] - 1) // 2
+        z = ops.gemm(x, w_taps, bias, taps_pad=pad)
+        scale, shift, mean, rstd = ops.bn_scale_shift(bn, z, training, save_stats=True)
         y = ops.affine_act(z, scale, shift, act)
-    return _pending("conv1d_bn_act", y, x, weight, bias, bn.weight, bn.bias)
+        ctx.save_for_backward(x, w_taps, z, scale, shift, mean, rstd)
+        ctx.meta = (act, training, pad, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w_taps, z, scale, shift, mean, rstd = ctx.saved_tensors
+        act, training, pad, has_bias = ctx.meta
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training)
+        dx, dw, db = _gemm_backward(gz, x, w_taps, pad, True, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db, dgamma, dbeta, None, None, None
 
 
-def glu_dwconv_bn_silu(h, dw_weight, dw_bias, bn, training):
-    C = dw_weight.shape[0]
-    hd, wd, bd = h.detach(), dw_weight.detach(), dw_bias.detach()
-    if not training:
-        scale, shift = ops.bn_scale_shift(bn, None, False)
-        y = ops.dwconv(hd, wd, bd, channels=C, glu=True, scale=scale, shift=shift)
-    else:
-        z = ops.dwconv(hd, wd, bd, channels=C, glu=True)
-        scale, shift = ops.bn_scale_shift(bn, z, True)
+def conv1d_bn_act(x, weight, bias, bn, act, training, dropout_p=0.0):
+    return dropout(_ConvBnAct.apply(x.contiguous(), weight, bias, bn.weight, bn.bias, bn, act, training), dropout_p)
+
+
+class _GluDwconvBnSilu(torch.autograd.Function):
+    """GLU → depthwise conv → BatchNorm1d → SiLU (torchaudio conformer.py:50-65)."""
+
+    @staticmethod
+    def forward(ctx, h, dw_w, dw_b, bn_w, bn_b, bn, training):
+        C = dw_w.shape[0]
+        z = ops.dwconv(h, dw_w, dw_b, channels=C, glu=True)
+        scale, shift, mean, rstd = ops.bn_scale_shift(bn, z, training, save_stats=True)
         y = ops.affine_act(z, scale, shift, "silu")
-    return _pending("glu_dwconv_bn_silu", y, h, dw_weight, dw_bias, bn.weight, bn.bias)
+        ctx.save_for_backward(h, dw_w, z, scale, shift, mean, rstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        h, dw_w, z, scale, shift, mean, rstd = ctx.saved_tensors
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, "silu", ctx.training)
+        dh, ddw, ddb = ops.dwconv_bwd(gz, h, dw_w, glu=True)
+        return dh, ddw, ddb, dgamma, dbeta, None, None
+
+
+def glu_dwconv_bn_silu(h, dw_w, dw_b, bn, training):
+    return _GluDwconvBnSilu.apply(h.contiguous(), dw_w, dw_b, bn.weight, bn.bias, bn, training)
+
+
+class _Dwconv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return ops.dwconv(x, weight, bias, channels=weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        return ops.dwconv_bwd(g.contiguous(), x, weight, glu=False)
 
 
 def dwconv(x, weight, bias):
-    y = ops.dwconv(x.detach(), weight.detach(), bias.detach(), channels=weight.shape[0])
-    return _pending("dwconv", y, x, weight, bias)
+    return _Dwconv.apply(x.contiguous(), weight, bias)
 
 
-def attention(qkv, lengths, heads, dropout=0.0):
-    assert not dropout, "dropout kernels pending"
-    return _pending("attention", ops.attention(qkv.detach(), lengths, heads), qkv)
+# ---------------------------------------------------------------------------------------------
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, lengths, heads, dropout_p):
+        seed = int(torch.randint(0, 2**31 - 1, (1,)).item()) if dropout_p else 0
+        out, lse = ops.attention(qkv, lengths, heads, want_lse=True, dropout_p=dropout_p, seed=seed)
+        ctx.save_for_backward(qkv, out, lse, lengths)
+        ctx.meta = (heads, dropout_p, seed)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        qkv, out, lse, lengths = ctx.saved_tensors
+        heads, p, seed = ctx.meta
+        return ops.attention_bwd(qkv, out, lse, g.contiguous(), lengths, heads, p, seed), None, None, None
+
+
+def attention(qkv, lengths, heads, dropout_p=0.0):
+    return _Attention.apply(qkv.contiguous(), lengths, heads, float(dropout_p))
+
+
+class _Rowdot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask):
+        ctx.save_for_backward(x, weight, mask)
+        return ops.rowdot(x, weight.reshape(-1), bias, mask)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight, mask = ctx.saved_tensors
+        dx, dw, db = ops.rowdot_bwd(g.contiguous(), x, weight.reshape(-1), mask)
+        return dx, dw.reshape(weight.shape), db, None
 
 
 def rowdot(x, weight, bias, mask):
-    y = ops.rowdot(x.detach(), weight.detach().reshape(-1), bias.detach(), mask)
-    return _pending("rowdot", y, x, weight, bias)
+    return _Rowdot.apply(x.contiguous(), weight, bias, mask)
+
+
+class _AlignerScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, prior, key_lens):
+        soft, logprob = ops.aligner_scores(q, k, prior, key_lens)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(q, k, prior, key_lens, soft, logprob)
+        return soft, logprob
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_soft, g_logprob):
+        q, k, prior, key_lens, soft, logprob = ctx.saved_tensors
+        if g_soft is None and g_logprob is None:
+            return None, None, None, None
+        dq, dk = ops.aligner_bwd(g_soft, g_logprob, soft, logprob, prior, key_lens, q, k)
+        return dq, dk, None, None
 
 
 def aligner_scores(q, k, prior, key_lens):
-    soft, logprob = ops.aligner_scores(q.detach(), k.detach(), prior, key_lens)
-    return _pending("aligner_scores", (soft, logprob), q, k)
+    return _AlignerScores.apply(q.contiguous(), k.contiguous(), prior, key_lens)
+
+
+# ---------------------------------------------------------------------------------------------
+class _LengthRegulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cum, total, width, inv_freq):
+        out, out_pos, mask, _ = ops.lr_gather(x, cum, total, width, inv_freq, want_out=True)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(cum)
+        ctx.meta = (x.shape[1], x.shape[2], width, out_pos is not None)
+        ctx.mark_non_differentiable(mask)
+        if out_pos is None:
+            return out, mask
+        return out, out_pos, mask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        (cum,) = ctx.saved_tensors
+        T, D, width, has_pos = ctx.meta
+        g_out = grads[0]
+        g_pos = grads[1] if has_pos else None
+        if g_out is None and g_pos is None:
+            return None, None, None, None, None
+        dx = ops.lr_bwd(g_out, g_pos, cum, T, D, width)
+        return dx, None, None, None, None
 
 
 def length_regulate(x, cum, total, width, inv_freq):
-    out, out_pos, mask, _ = ops.lr_gather(x.detach(), cum, total, width, inv_freq, want_out=True)
-    out, out_pos = _pending("length_regulate", (out, out_pos), x)
+    if torch.is_grad_enabled() and x.requires_grad:
+        r = _LengthRegulate.apply(x.contiguous(), cum, total, width, inv_freq)
+        return (r[0], None, r[1]) if inv_freq is None else r
+    out, out_pos, mask, _ = ops.lr_gather(x, cum, total, width, inv_freq, want_out=True)
     return out, out_pos, mask
 
 
+class _BucketizeEmbedAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, v, scale, bins):
+        y, ids, _ = ops.bucketize_embed_add(v, bins, table, x, scale=scale, want_ids=True)
+        ctx.save_for_backward(ids)
+        ctx.table_shape = table.shape
+        ctx.mark_non_differentiable(ids)
+        return y, ids
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _gids):
+        (ids,) = ctx.saved_tensors
+        g = g.contiguous()
+        dtable = None
+        if ctx.needs_input_grad[1]:
+            dtable = torch.zeros(ctx.table_shape, dtype=torch.float32, device=g.device)
+            ops.scatter_add_rows(dtable, g, ids)
+        return g, dtable, None, None, None
+
+
 def bucketize_embed_add(v, scale, bins, table, x, return_scaled=False):
-    y, ids, vs = ops.bucketize_embed_add(v.detach().contiguous(), bins.detach(), table.detach(), x.detach(), scale=scale,
-                                         want_ids=True, want_scaled=return_scaled)
-    y = _pending("bucketize_embed_add", y, x, table)
-    if return_scaled:
-        return y, ids, _pending("scale", vs, v)
+    if return_scaled:  # inference: the scaled prediction is returned; no gradient flows here
+        y, ids, vs = ops.bucketize_embed_add(v.detach().contiguous(), bins, _d(table), _d(x), scale=scale, want_ids=True, want_scaled=True)
+        return y, ids, vs
+    if torch.is_grad_enabled() and (x.requires_grad or table.requires_grad):
+        return _BucketizeEmbedAdd.apply(x.contiguous(), table, v.detach().contiguous(), float(scale), bins.detach())
+    y, ids, _ = ops.bucketize_embed_add(v.detach().contiguous(), bins, table, x, scale=scale, want_ids=True)
     return y, ids
 
 
 def embedding_lookup(ids, table):
-    return _pending("embedding_lookup", ops.gather_rows(table.detach(), ids), table)
+    return _EmbeddingLookup.apply(table, ids)
+
+
+class _EmbeddingLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.save_for_backward(ids)
+        ctx.table_shape = table.shape
+        return ops.gather_rows(table, ids)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        dtable = torch.zeros(ctx.table_shape, dtype=torch.float32, device=g.device)
+        ops.scatter_add_rows(dtable, g.contiguous(), ids)
+        return dtable, None
+
+
+class _Scale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, factor):
+        ctx.factor = factor
+        return ops.axpby(x, factor)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return ops.axpby(g.contiguous(), ctx.factor), None
 
 
 def scale(x, factor):
-    return _pending("scale", ops.axpby(x.detach(), float(factor)), x)
+    return _Scale.apply(x.contiguous(), float(factor))
+
+
+class _EmbedPosenc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, text, inv_freq, lens, padding_idx):
+        emb, x = ops.embed_posenc(text, table, inv_freq, lens)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(text)
+        ctx.meta = (table.shape, -1 if padding_idx is None else int(padding_idx))
+        return emb, x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_emb, g_x):
+        (text,) = ctx.saved_tensors
+        shape, pad = ctx.meta
+        ref = g_emb if g_emb is not None else g_x
+        if ref is None:
+            return None, None, None, None, None
+        dtable = torch.zeros(shape, dtype=torch.float32, device=ref.device)
+        g1 = g_x if g_x is not None else g_emb
+        g2 = g_emb if (g_x is not None and g_emb is not None) else None
+        ops.scatter_add_rows(dtable, g1.contiguous(), text, None if g2 is None else g2.contiguous(), skip_id=pad)
+        return dtable, None, None, None, None
 
 
 def embed_posenc(text, table, inv_freq, lens, padding_idx):
-    emb, x = ops.embed_posenc(text.contiguous(), table.detach(), inv_freq, lens)
-    return _pending("embed_posenc", (emb, x), table)
+    text = text.contiguous()
+    if text.dtype != torch.int32:
+        text = text.to(torch.int32)
+    if torch.is_grad_enabled() and table.requires_grad:
+        return _EmbedPosenc.apply(table, text, inv_freq, lens, padding_idx)
+    return ops.embed_posenc(text, table, inv_freq, lens)
+
+
+class _AddPosenc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inv_freq, lens):
+        return ops.add_posenc(x, inv_freq, lens)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
 
 
 def add_posenc(x, inv_freq, lens):
-    return _pending("add_posenc", ops.add_posenc(x.detach(), inv_freq, lens), x)
+    return _AddPosenc.apply(x.contiguous(), inv_freq, lens)
+
+
+class _AddRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_rows, *rows_and_ids):
+        rows = rows_and_ids[:n_rows]
+        ids = rows_and_ids[n_rows:]
+        ctx.save_for_backward(*[i for i in ids if i is not None])
+        ctx.meta = (n_rows, [r.shape for r in rows], [i is not None for i in ids])
+        return ops.add_rows(x, list(zip([r.contiguous() for r in rows], ids)))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        n_rows, shapes, has_ids = ctx.meta
+        saved = list(ctx.saved_tensors)
+        g = g.contiguous()
+        grads = []
+        for k in range(n_rows):
+            ids = saved.pop(0) if has_ids[k] else None
+            if ctx.needs_input_grad[2 + k]:
+                d = torch.zeros(shapes[k], dtype=torch.float32, device=g.device)
+                ops.rows_sum_scatter(d, g, ids)
+                grads.append(d)
+            else:
+                grads.append(None)
+        return (g, None, *grads, *([None] * n_rows))
 
 
 def add_rows(x, rows):
-    y = ops.add_rows(x.detach(), [(r.detach().contiguous(), i) for r, i in rows])
-    return _pending("add_rows", y, x, *[r for r, _ in rows])
+    return _AddRows.apply(x.contiguous(), len(rows), *[r for r, _ in rows], *[i for _, i in rows])
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.axpby(a, 1.0, b, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
 
 
 def add(a, b):
-    return _pending("add", ops.axpby(a.detach(), 1.0, b.detach(), 1.0), a, b)
+    return _Add.apply(a.contiguous(), b.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+class _MaskedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, kind, weight, log1p_int_target):
+        ctx.save_for_backward(pred, target, mask)
+        ctx.meta = (kind, weight, log1p_int_target)
+        return ops.masked_loss_fwd(pred, target, mask, kind, weight, log1p_int_target)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        pred, target, mask = ctx.saved_tensors
+        kind, weight, log1p = ctx.meta
+        return ops.masked_loss_bwd(pred, target, mask, kind, weight, g.contiguous(), log1p), None, None, None, None, None
 
 
 def masked_loss(pred, target, mask, kind, weight, log1p_int_target=False):
-    loss = ops.masked_loss_fwd(pred.detach(), target.detach(), mask, kind, weight, log1p_int_target)
-    return _pending("masked_loss", loss, pred)
+    return _MaskedLoss.apply(pred.contiguous(), target.detach().contiguous(), mask, kind, float(weight), bool(log1p_int_target))
+
+
+class _BinLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hard, soft, eps):
+        loss, sums = ops.bin_loss_fwd(hard, soft, eps)
+        ctx.save_for_backward(hard, soft, sums)
+        ctx.eps = eps
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        hard, soft, sums = ctx.saved_tensors
+        return None, ops.bin_loss_bwd(hard, soft, ctx.eps, sums, g.contiguous()), None
 
 
 def attn_bin_loss(hard, soft, eps=1e-12):
-    loss, _ = ops.bin_loss_fwd(hard, soft.detach(), eps)
-    return _pending("attn_bin_loss", loss, soft)
+    return _BinLoss.apply(hard.detach().contiguous(), soft.contiguous(), float(eps))
 
 
 def tanh_row(table, index):
-    return _pending("tanh_row", ops.tanh(table.detach()[index : index + 1].contiguous()), table)
+    return ops.tanh(table.detach()[index: index + 1].contiguous())

@@ -18,7 +18,7 @@ constexpr int ABQ = 64, ABK = 32;
 template <int HD>
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ lens, int L, int H, float scale,
-                      float* __restrict__ out, float* __restrict__ lse_out) {
+                      float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ lse_out) {
     constexpr int QS = HD + 4, PS = ABK + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;                 // [ABQ][QS]
@@ -29,6 +29,7 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
     const int D = H * HD, ld = 3 * D;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int len = min(lens[b], L);
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const float* base = qkv + (size_t)b * L * ld + h * HD;
 
     // stage the query tile (rows past L are zero)
@@ -103,8 +104,9 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const float p = expf(s[i][j] - m_use);
-                rs += p;
-                Ps[(ty * 4 + i) * PS + tx + 16 * j] = p;
+                rs += p;  // the softmax normaliser uses the un-dropped probabilities
+                Ps[(ty * 4 + i) * PS + tx + 16 * j] =
+                    p * attn_keep(seed, drop_p, inv_keep, b, h, q0 + ty * 4 + i, k0 + tx + 16 * j, H, L);
             }
 #pragma unroll
             for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
@@ -158,10 +160,11 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
 
 using namespace fs2k;
 
-extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float* out,
-                                  float* lse_out, fs2k_stream_t stream) {
+extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
+                                  long seed, float* out, float* lse_out, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && H > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(head_dim == 64 || head_dim == 128, FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FS2K_ERR_BAD_SHAPE);
     if (B == 0 || L == 0) return FS2K_OK;
     FS2K_REQUIRE(qkv && lens && out, FS2K_ERR_NULL);
     const float scale = 1.0f / sqrtf((float)head_dim);
@@ -175,10 +178,10 @@ extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int 
             if (e != cudaSuccess) return fs2k_set_cuda_error(e);
             set = true;
         }
-        attention_simt_kernel<128><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, out, lse_out);
+        attention_simt_kernel<128><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     } else {
         const int smem = (ABQ * 68 + ABK * 68 + ABK * 64 + ABQ * (ABK + 4)) * 4;
-        attention_simt_kernel<64><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, out, lse_out);
+        attention_simt_kernel<64><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -55,4 +55,21 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
+// counter-based uniform in [0,1): splitmix64 finaliser of (seed, index).  Dropout masks are regenerated
+// from the seed in the backward pass instead of being stored.
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long i) {
+    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + i + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// scaled keep mask of attention-probability dropout for element (b,h,q,k)
+__device__ __forceinline__ float attn_keep(unsigned long long seed, float p, float inv_keep, int b, int h, int q, int k,
+                                           int H, int L) {
+    if (p <= 0.f) return 1.f;
+    const unsigned long long idx = (((unsigned long long)b * H + h) * L + q) * L + k;
+    return hash_uniform(seed, idx) >= p ? inv_keep : 0.f;
+}
+
 }  // namespace fs2k

@@ -11,10 +11,11 @@
 // thread issues four K=8 tf32 MMAs per stage.  `passes = 3` adds the split-accumulate 3×TF32 scheme
 // (big·big + big·small + small·big, small = x − tf32(x)) that restores fp32-level accuracy.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = operand splitter helper,
-// 4-7 = TMEM → registers → staging tile in shared memory (per-column epilogue math); then all eight
-// warps store the tile with fully coalesced 16-byte accesses, adding the residual, the row mask and,
-// when requested, the LayerNorm of the row (a row lives in one warp, so mean/var are two shuffles).
+// Warp roles (12 warps): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-11 = operand splitter
+// during the main loop (3×TF32 only), then TMEM → registers → raw staging tile in shared memory; finally
+// all twelve warps run the store pass: per-column math (bias, folded BatchNorm, activation, alpha),
+// residual, row mask and, when requested, the LayerNorm of the row (a row lives in one warp, so mean and
+// variance are two shuffle reductions), with fully coalesced 16-byte global accesses, four rows in flight.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ namespace fs2k {
 constexpr int TC_BM = 128;      // rows per tile == TMEM lanes
 constexpr int TC_BK = 32;       // fp32 elements per 128-byte swizzle atom
 template <int PASSES> struct TcStages { static constexpr int value = PASSES == 3 ? 2 : 4; };  // 3×TF32 keeps a second copy of every tile
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
 
 struct TcEpilogue {
     const float* bias; const float* scale; const float* shift;
@@ -123,6 +124,32 @@ __device__ __forceinline__ void split_small(const float4* src, float4* dst, int 
     }
 }
 
+// finished-row math shared by the store pass: v = act((acc + bias)·scale + shift)·alpha
+__device__ __forceinline__ float4 tc_colmath(float4 a, const float4& bias, const float4& sc, const float4& sh, int act, float alpha) {
+    a.x = tc_act((a.x + bias.x) * sc.x + sh.x, act) * alpha;
+    a.y = tc_act((a.y + bias.y) * sc.y + sh.y, act) * alpha;
+    a.z = tc_act((a.z + bias.z) * sc.z + sh.z, act) * alpha;
+    a.w = tc_act((a.w + bias.w) * sc.w + sh.w, act) * alpha;
+    return a;
+}
+__device__ __forceinline__ float4 tc_ln_apply(const float4& v, float mean, float rstd, const float4& g, const float4& b) {
+    float4 o;
+    o.x = (v.x - mean) * rstd * g.x + b.x;
+    o.y = (v.y - mean) * rstd * g.y + b.y;
+    o.z = (v.z - mean) * rstd * g.z + b.z;
+    o.w = (v.w - mean) * rstd * g.w + b.w;
+    return o;
+}
+__device__ __forceinline__ float tc_sum4(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
+__device__ __forceinline__ float tc_sq4(const float4& v, float m) {
+    const float a = v.x - m, b = v.y - m, c = v.z - m, d = v.w - m;
+    return (a * a + b * b) + (c * c + d * d);
+}
+
+constexpr int TC_EPI_WARPS = 8;                 // warps 4..11: operand split (3×TF32) and TMEM → staging
+constexpr int TC_WARPS = TC_THREADS / 32;       // 12
+constexpr int TC_ROWS_PER_ITER = 4;             // rows a warp keeps in flight in the store pass
+
 template <int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -131,7 +158,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int TC_STAGES = TcStages<PASSES>::value;
     __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_split[TC_STAGES], s_tmem_full;
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_colp[3][256];
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = block_n * TC_BK * 4;
@@ -143,17 +169,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nk = (K + TC_BK - 1) / TC_BK;
     const int iters = taps * nk;
 
-    // per-column epilogue parameters → shared memory
-    for (int c = threadIdx.x; c < block_n; c += TC_THREADS) {
-        s_colp[0][c] = ep.bias ? ep.bias[n0 + c] : 0.f;
-        s_colp[1][c] = ep.scale ? ep.scale[n0 + c] : 1.f;
-        s_colp[2][c] = ep.scale ? ep.shift[n0 + c] : 0.f;
-    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
-            mbar_init(smem_u32(&s_split[s]), 32);
+            mbar_init(smem_u32(&s_split[s]), TC_EPI_WARPS * 32);
         }
         mbar_init(smem_u32(&s_tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,36 +226,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_commit(smem_u32(&s_tmem_full));
         }
-    } else if (warp == 3) {
+    } else if (warp >= 4) {
+        const int et = threadIdx.x - 128;  // 0..255 among the epilogue warps
         if (PASSES == 3) {
-            // ================= operand splitter (3×TF32): small parts of A and W next to the originals ==========
+            // ===== operand splitter (3×TF32): small parts of A and W written next to the originals =====
             for (int it = 0; it < iters; ++it) {
                 const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 mbar_wait(smem_u32(&s_full[s]), ph);
                 const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
                 float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes + b_bytes);
-                split_small(src, dst, (a_bytes + b_bytes) / 16, lane, 32);
+                split_small(src, dst, (a_bytes + b_bytes) / 16, et, TC_EPI_WARPS * 32);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes → visible to the MMA proxy
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_split[s])) : "memory");
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue stage 1: TMEM → registers → per-column math → staging tile =================
+        // ===== epilogue stage 1: raw accumulators TMEM → registers → staging tile (row = TMEM lane) =====
         mbar_wait(smem_u32(&s_tmem_full), 0);
         tc_fence_after();
         const int q = warp & 3;              // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;    // two warps share a quadrant and alternate 16-column chunks
         const int row = q * 32 + lane;
         const int pitch = block_n + 4;
         float* stag = reinterpret_cast<float*>(smem);
-        for (int c0 = 0; c0 < block_n; c0 += 16) {
+        for (int c0 = half * 16; c0 < block_n; c0 += 32) {
             float v[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = v[j] + s_colp[0][c0 + j];
-                x = x * s_colp[1][c0 + j] + s_colp[2][c0 + j];
-                v[j] = tc_act(x, ep.act) * ep.alpha;
-            }
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(stag + (size_t)row * pitch + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -244,89 +259,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncthreads();
 
-    // ================= epilogue stage 2: coalesced stores (+ residual, row mask, LayerNorm) =================
+    // ===== epilogue stage 2 (all warps): column math, residual, row mask, LayerNorm, coalesced 16-byte stores =====
     {
         const int pitch = block_n + 4;
         const float* stag = reinterpret_cast<const float*>(smem);
-        const int nv = block_n >> 2;  // float4 per row (≤ 64)
-        const bool do_ln = ep.ln_out != nullptr;
-        for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
-            const int l = l0 + r;
-            if (l >= L) break;
-            const long m = (long)b_idx * L + l;
-            if (m >= M_total) break;
-            const float rm = ep.row_mask ? (ep.row_mask[m] ? 1.f : 0.f) : 1.f;
-            float4 val[2];
-            float sum = 0.f;
+        const int nv = block_n >> 2;  // float4 per row (≤ 64): lane owns float4 columns lane and lane+32
+        const bool has[2] = {lane < nv, lane + 32 < nv};
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 bias4[2], sc4[2], sh4[2], g1[2], b1[2], g2[2], b2[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int qv = lane + 32 * j;
-                if (qv < nv) {
-                    float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
-                    if (ep.residual) {
-                        const float4 rr = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n0 + qv * 4);
-                        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-                    }
-                    if (ep.row_mask) { v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm; }
-                    if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
-                    val[j] = v;
-                    sum += (v.x + v.y) + (v.z + v.w);
-                } else {
-                    val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            if (do_ln) {
-                // LayerNorm over the N = block_n columns of this row (held by this warp)
-                const float inv_n = 1.0f / (float)block_n;
-                float mean = warp_sum(sum) * inv_n;
-                float ss = 0.f;
+        for (int j = 0; j < 2; ++j) {
+            const int qv = lane + 32 * j;
+            bias4[j] = (has[j] && ep.bias) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + qv) : zero4;
+            sc4[j] = (has[j] && ep.scale) ? __ldg(reinterpret_cast<const float4*>(ep.scale + n0) + qv) : one4;
+            sh4[j] = (has[j] && ep.scale) ? __ldg(reinterpret_cast<const float4*>(ep.shift + n0) + qv) : zero4;
+            g1[j] = (has[j] && ep.ln_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + qv) : one4;
+            b1[j] = (has[j] && ep.ln_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + qv) : zero4;
+            g2[j] = (has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma) + qv) : one4;
+            b2[j] = (has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_beta) + qv) : zero4;
+        }
+        const int rows_valid = (int)min((long)TC_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
+        const float inv_n = 1.0f / (float)block_n;
+        for (int rb = warp; rb < rows_valid; rb += TC_WARPS * TC_ROWS_PER_ITER) {
+            float4 val[TC_ROWS_PER_ITER][2], res[TC_ROWS_PER_ITER][2];
+            float rm[TC_ROWS_PER_ITER];
+            // issue every global read of the row group before using any of them
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    if (lane + 32 * j < nv) {
-                        const float a = val[j].x - mean, b = val[j].y - mean, c = val[j].z - mean, d = val[j].w - mean;
-                        ss += (a * a + b * b) + (c * c + d * d);
-                    }
-                float rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
-                float sum2 = 0.f;
+            for (int u = 0; u < TC_ROWS_PER_ITER; ++u) {
+                const int r = rb + u * TC_WARPS;
+                const long m = (long)b_idx * L + l0 + r;
+                rm[u] = 1.f;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int qv = lane + 32 * j;
-                    if (qv < nv) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + qv);
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + qv);
-                        float4 o;
-                        o.x = (val[j].x - mean) * rstd * g.x + bb.x;
-                        o.y = (val[j].y - mean) * rstd * g.y + bb.y;
-                        o.z = (val[j].z - mean) * rstd * g.z + bb.z;
-                        o.w = (val[j].w - mean) * rstd * g.w + bb.w;
-                        *reinterpret_cast<float4*>(ep.ln_out + (size_t)m * ep.ld_ln + qv * 4) = o;
-                        val[j] = o;
-                        sum2 += (o.x + o.y) + (o.z + o.w);
+                    res[u][j] = zero4;
+                    if (r < rows_valid && has[j] && ep.residual)
+                        res[u][j] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n0 + (lane + 32 * j) * 4);
+                }
+                if (r < rows_valid && ep.row_mask) rm[u] = ep.row_mask[m] ? 1.f : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < TC_ROWS_PER_ITER; ++u) {
+                const int r = rb + u * TC_WARPS;
+                if (r >= rows_valid) break;  // warp-uniform
+                const long m = (long)b_idx * L + l0 + r;
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (has[j]) {
+                        const int qv = lane + 32 * j;
+                        float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
+                        v = tc_colmath(v, bias4[j], sc4[j], sh4[j], ep.act, ep.alpha);
+                        v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
+                        v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];
+                        if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
+                        val[u][j] = v;
+                        sum += tc_sum4(v);
+                    } else {
+                        val[u][j] = zero4;
                     }
                 }
-                if (ep.ln2_out) {  // second LayerNorm chained on the first one's output
-                    mean = warp_sum(sum2) * inv_n;
-                    ss = 0.f;
+                if (ep.ln_out) {  // LayerNorm over the block_n == N columns of this row (one warp holds the row)
+                    float mean = warp_sum(sum) * inv_n;
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) if (has[j]) ss += tc_sq4(val[u][j], mean);
+                    float rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
+                    float sum2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
-                        if (lane + 32 * j < nv) {
-                            const float a = val[j].x - mean, b = val[j].y - mean, c = val[j].z - mean, d = val[j].w - mean;
-                            ss += (a * a + b * b) + (c * c + d * d);
+                        if (has[j]) {
+                            const float4 o = tc_ln_apply(val[u][j], mean, rstd, g1[j], b1[j]);
+                            *reinterpret_cast<float4*>(ep.ln_out + (size_t)m * ep.ld_ln + (lane + 32 * j) * 4) = o;
+                            val[u][j] = o;
+                            sum2 += tc_sum4(o);
                         }
-                    rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
+                    if (ep.ln2_out) {  // second LayerNorm chained on the first one's output
+                        mean = warp_sum(sum2) * inv_n;
+                        ss = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int qv = lane + 32 * j;
-                        if (qv < nv) {
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma) + qv);
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln2_beta) + qv);
-                            float4 o;
-                            o.x = (val[j].x - mean) * rstd * g.x + bb.x;
-                            o.y = (val[j].y - mean) * rstd * g.y + bb.y;
-                            o.z = (val[j].z - mean) * rstd * g.z + bb.z;
-                            o.w = (val[j].w - mean) * rstd * g.w + bb.w;
-                            *reinterpret_cast<float4*>(ep.ln2_out + (size_t)m * ep.ld_ln + qv * 4) = o;
-                        }
+                        for (int j = 0; j < 2; ++j) if (has[j]) ss += tc_sq4(val[u][j], mean);
+                        rstd = 1.0f / sqrtf(warp_sum(ss) * inv_n + ep.ln_eps);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (has[j])
+                                *reinterpret_cast<float4*>(ep.ln2_out + (size_t)m * ep.ld_ln + (lane + 32 * j) * 4) =
+                                    tc_ln_apply(val[u][j], mean, rstd, g2[j], b2[j]);
                     }
                 }
             }
@@ -381,7 +398,14 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     FS2K_REQUIRE(A && W && (C || ln_out), FS2K_ERR_NULL);
     FS2K_REQUIRE(!scale || shift, FS2K_ERR_NULL);
     FS2K_REQUIRE((ldc & 3) == 0 && (!residual || (ldr & 3) == 0), FS2K_ERR_UNSUPPORTED);
-    const int block_n = N <= 256 ? N : ((N % 256) == 0 ? 256 : 128);
+    int block_n = N <= 256 ? N : ((N % 256) == 0 ? 256 : 128);
+    if (!ln_out) {
+        // small-M problems (encoder, predictors: ≤ 20 row tiles) are latency-bound per CTA: narrow the
+        // column tile until the grid covers most of the 148 SMs
+        const long tiles_m = (taps == 1) ? (M + TC_BM - 1) / TC_BM : (long)B * ((L + TC_BM - 1) / TC_BM);
+        while (block_n > 32 && (block_n / 2) % 16 == 0 && N % (block_n / 2) == 0 && tiles_m * (N / block_n) < 100)
+            block_n /= 2;
+    }
     FS2K_REQUIRE(!ln_out || (block_n == N && ln_gamma && ln_beta), FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(!ln2_out || (ln_out && ln2_gamma && ln2_beta), FS2K_ERR_UNSUPPORTED);
     EncodeTiledFn encode = get_encode();

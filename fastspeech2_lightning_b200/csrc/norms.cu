@@ -147,8 +147,8 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const int q = (int)(i % C4);
         const float4 v = reinterpret_cast<const float4*>(z)[i];
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
+        const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 sh = scale ? __ldg(reinterpret_cast<const float4*>(shift) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         float o[4] = {v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -221,7 +221,7 @@ extern "C" int fs2k_affine_act(const float* z, const float* scale, const float* 
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
     if (M == 0) return FS2K_OK;
-    FS2K_REQUIRE(z && scale && shift && y, FS2K_ERR_NULL);
+    FS2K_REQUIRE(z && y && (!scale || shift), FS2K_ERR_NULL);  // scale == NULL: plain activation
     long g = (M * (C >> 2) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     affine_act_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(z, scale, shift, act, residual, M, C, y);

@@ -1,0 +1,85 @@
+// Training-step tail over one flat parameter buffer: global gradient norm, norm clipping and AdamW in two
+// launches (reference: torch.optim.AdamW at fs2/model.py:530-537, gradient_clip_val = 1.0 at fs2/cli/train.py:38,
+// which Lightning applies as clip_grad_norm_).  The clip coefficient stays on the device — no host sync.
+#include "common.cuh"
+
+namespace fs2k {
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long N, double* __restrict__ out) {
+    double acc = 0.0;
+    const long N4 = N >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long i = N4 << 2; i < N; ++i) acc += (double)g[i] * g[i];
+    acc = warp_sum_d(acc);
+    __shared__ double s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += s[w];
+        atomicAdd(out, t);
+    }
+}
+
+// clip: g ← g · min(1, max_norm / (‖g‖ + 1e-6)) (skipped when sumsq is null), then decoupled-weight-decay Adam
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long N,
+             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
+             float grad_scale, const double* __restrict__ sumsq) {
+    float clip = grad_scale;
+    if (sumsq) {
+        const float total = (float)sqrt(sumsq[0]) * grad_scale;
+        const float c = max_norm / (total + 1e-6f);
+        clip *= c < 1.f ? c : 1.f;
+    }
+    const float step_size = lr / bc1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * clip;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] * (1.f - lr * wd) - step_size * (mi / denom);
+    }
+}
+
+}  // namespace fs2k
+
+using namespace fs2k;
+
+extern "C" int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t stream) {
+    FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
+    FS2K_REQUIRE(g && out, FS2K_ERR_NULL);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+    if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    if (N == 0) return FS2K_OK;
+    long grid = (N / 4 + 255) / 256;
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid < 1) grid = 1;
+    sumsq_kernel<<<(int)grid, 256, 0, s>>>(g, N, out);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float lr, float beta1, float beta2,
+                               float eps, float weight_decay, long step, float max_norm, float grad_scale,
+                               const double* sumsq, fs2k_stream_t stream) {
+    FS2K_REQUIRE(N >= 0 && step >= 1, FS2K_ERR_BAD_SHAPE);
+    if (N == 0) return FS2K_OK;
+    FS2K_REQUIRE(p && g && m && v, FS2K_ERR_NULL);
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    long grid = (N + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    adamw_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                             bc2_sqrt, max_norm, grad_scale, sumsq);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}

@@ -292,7 +292,12 @@ class FastSpeech2(_Base):
 
     def configure_optimizers(self):
         o = self.config.training.optimizer
-        self.optimizer = torch.optim.AdamW(self.parameters(), o.learning_rate, betas=o.betas, eps=o.eps,
-                                           weight_decay=o.weight_decay)
+        # Same update rule and hyper-parameters as the reference's torch.optim.AdamW (model.py:530-537), run as one
+        # fused launch over a flat parameter buffer.  `fused_grad_clip` (e.g. 1.0, the value fs2/cli/train.py:38
+        # hands to Lightning) folds clip_grad_norm_ into the same launch; leave it None when the trainer clips.
+        from ..optim import FusedAdamW
+
+        self.optimizer = FusedAdamW(self.parameters(), o.learning_rate, betas=tuple(o.betas), eps=o.eps,
+                                    weight_decay=o.weight_decay, max_grad_norm=getattr(self, "fused_grad_clip", None))
         self.scheduler = NoamLR(self.optimizer, o.warmup_steps)
         return [self.optimizer], [{"scheduler": self.scheduler, "interval": "step"}]

@@ -384,13 +384,13 @@ def rowdot(x, w, b=None, mask=None):
     return y
 
 
-def attention(qkv, lens, heads: int, want_lse: bool = False):
+def attention(qkv, lens, heads: int, want_lse: bool = False, dropout_p: float = 0.0, seed: int = 0):
     qkv, lens = _f32(qkv, "qkv"), _i32(lens, "lens")
     B, L, D3 = qkv.shape
     D = D3 // 3
     out = torch.empty((B, L, D), dtype=torch.float32, device=qkv.device)
     lse = torch.empty((B, heads, L), dtype=torch.float32, device=qkv.device) if want_lse else None
-    check(lib().fs2k_attention_f32(_p(qkv), _p(lens), B, L, heads, D // heads, _p(out), _p(lse), _stream()), "fs2k_attention_f32")
+    check(lib().fs2k_attention_f32(_p(qkv), _p(lens), B, L, heads, D // heads, float(dropout_p), int(seed), _p(out), _p(lse), _stream()), "fs2k_attention_f32")
     _count()
     return (out, lse) if want_lse else out
 
@@ -490,9 +490,181 @@ def gather_rows(table, ids):
     return out
 
 
+def dropout(x, p: float, seed: int):
+    x = _f32(x, "x")
+    y = torch.empty_like(x)
+    check(lib().fs2k_dropout(_p(x), float(p), int(seed), x.numel(), _p(y), _stream()), "fs2k_dropout")
+    _count()
+    return y
+
+
 def tanh(x):
     x = _f32(x, "x")
     y = torch.empty_like(x)
     check(lib().fs2k_tanh(_p(x), x.numel(), _p(y), _stream()), "fs2k_tanh")
     _count()
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# backward kernels
+# ---------------------------------------------------------------------------------------------
+_ACT_BWD_MODE = {None: 0, "none": 0, "relu": 1, "silu": 2, "tanh": 3}
+
+
+def act_bwd(g, aux, act, alpha: float = 1.0, row_mask=None):
+    g = _f32(g, "g")
+    C = g.shape[-1]
+    M = g.numel() // C
+    gz = torch.empty_like(g)
+    if row_mask is not None:
+        row_mask = row_mask.contiguous()
+    check(lib().fs2k_act_bwd(_p(g), _p(aux), _ACT_BWD_MODE[act], float(alpha), _p(row_mask), M, C, _p(gz), _stream()), "fs2k_act_bwd")
+    _count()
+    return gz
+
+
+def colsum(z):
+    z = _f32(z, "z")
+    C = z.shape[-1]
+    out = torch.empty((C,), dtype=torch.float32, device=z.device)
+    check(lib().fs2k_colsum(_p(z), z.numel() // C, C, _p(out), _stream()), "fs2k_colsum")
+    _count()
+    return out
+
+
+def weight_taps_transposed(w_taps):
+    """[taps,N,K] → [taps,K,N] with reversed taps (weights of the transposed convolution)."""
+    w_taps = _f32(w_taps, "w_taps")
+    taps, N, K = w_taps.shape
+    out = torch.empty((taps, K, N), dtype=torch.float32, device=w_taps.device)
+    check(lib().fs2k_repack_weight_t(_p(w_taps), N, K, taps, _p(out), _stream()), "fs2k_repack_weight_t")
+    _count()
+    return out
+
+
+def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool):
+    """dW for y = conv(x, W): g [B,L,N], x [B,L,K] → [N,K,taps] (conv_layout) or [N,K]."""
+    g, x = _f32(g, "g"), _f32(x, "x")
+    if g.dim() == 2:
+        B, L = 1, g.shape[0]
+    else:
+        B, L = g.shape[0], g.shape[1]
+    N, K = g.shape[-1], x.shape[-1]
+    dw = torch.empty((taps, N, K), dtype=torch.float32, device=g.device)
+    check(lib().fs2k_gemm_wgrad(_p(g), N, _p(x), K, B, L, N, K, taps, pad, _p(dw), _stream()), "fs2k_gemm_wgrad")
+    _count()
+    if not conv_layout:
+        return dw[0]
+    if taps == 1:
+        return dw.reshape(N, K, 1)
+    out = torch.empty((N, K, taps), dtype=torch.float32, device=g.device)
+    check(lib().fs2k_unpack_conv_weight(_p(dw), N, K, taps, _p(out), _stream()), "fs2k_unpack_conv_weight")
+    _count()
+    return out
+
+
+def layernorm_bwd(g, x, mean, rstd, gamma):
+    g, x = _f32(g, "g"), _f32(x, "x")
+    D = x.shape[-1]
+    M = x.numel() // D
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((D,), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty((D,), dtype=torch.float32, device=x.device)
+    check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, _p(dx), _p(dgamma), _p(dbeta), _stream()), "fs2k_layernorm_bwd")
+    _count()
+    return dx, dgamma, dbeta
+
+
+def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool):
+    g, z = _f32(g, "g"), _f32(z, "z")
+    C = z.shape[-1]
+    M = z.numel() // C
+    sums = torch.empty((2 * C,), dtype=torch.float64, device=z.device)
+    gz = torch.empty_like(z)
+    dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
+    dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
+    check(lib().fs2k_bn_act_bwd(_p(g), _p(z), _p(scale), _p(shift), _p(mean), _p(rstd), _ACTS[act], int(training), M, C,
+                                _p(sums), _p(gz), _p(dgamma), _p(dbeta), _stream()), "fs2k_bn_act_bwd")
+    _count(2)
+    return gz, dgamma, dbeta
+
+
+def attention_bwd(qkv, out, lse, dout, lens, heads: int, dropout_p: float = 0.0, seed: int = 0):
+    qkv, out, dout = _f32(qkv, "qkv"), _f32(out, "out"), _f32(dout, "dout")
+    B, L, D3 = qkv.shape
+    D = D3 // 3
+    delta = torch.empty((B, heads, L), dtype=torch.float32, device=qkv.device)
+    dqkv = torch.empty_like(qkv)
+    check(lib().fs2k_attention_bwd_f32(_p(qkv), _p(out), _p(lse), _p(dout), _p(_i32(lens)), B, L, heads, D // heads, float(dropout_p), int(seed), _p(delta), _p(dqkv), _stream()), "fs2k_attention_bwd_f32")
+    _count(3)
+    return dqkv
+
+
+def dwconv_bwd(gz, x, weight, glu: bool, want_bias: bool = True):
+    gz, x = _f32(gz, "gz"), _f32(x, "x")
+    B, L, ldx = x.shape
+    C, _, K = weight.shape
+    dx = torch.empty_like(x)
+    dw = torch.empty_like(weight)
+    db = torch.empty((C,), dtype=torch.float32, device=x.device) if want_bias else None
+    check(lib().fs2k_dwconv_bwd(_p(gz), _p(x), ldx, B, L, C, _p(_f32(weight)), K, int(glu), _p(dx), _p(dw), _p(db), _stream()), "fs2k_dwconv_bwd")
+    _count()
+    return dx, dw, db
+
+
+def rowdot_bwd(g, x, w, mask):
+    g, x = _f32(g, "g"), _f32(x, "x")
+    D = x.shape[-1]
+    M = x.numel() // D
+    dx = torch.empty_like(x)
+    dw = torch.empty((D,), dtype=torch.float32, device=x.device)
+    db = torch.empty((1,), dtype=torch.float32, device=x.device)
+    if mask is not None:
+        mask = mask.contiguous()
+    check(lib().fs2k_rowdot_bwd(_p(g), _p(x), _p(_f32(w)), _p(mask), M, D, _p(dx), _p(dw), _p(db), _stream()), "fs2k_rowdot_bwd")
+    _count()
+    return dx, dw, db
+
+
+def lr_bwd(g_out, g_out_pos, cum, T: int, D: int, F_out: int):
+    B = cum.shape[0]
+    ref = g_out if g_out is not None else g_out_pos
+    dx = torch.empty((B, T, D), dtype=torch.float32, device=ref.device)
+    g1 = _f32(g_out) if g_out is not None else None
+    g2 = _f32(g_out_pos) if g_out_pos is not None else None
+    check(lib().fs2k_lr_bwd(_p(g1), _p(g2), _p(cum), B, T, D, F_out, _p(dx), _stream()), "fs2k_lr_bwd")
+    _count()
+    return dx
+
+
+def scatter_add_rows(dtable, g1, ids, g2=None, skip_id: int = -1):
+    g1 = _f32(g1, "g1")
+    if g2 is not None:
+        g2 = _f32(g2, "g2")
+    ids = ids.contiguous()
+    D = dtable.shape[1]
+    check(lib().fs2k_scatter_add_rows(_p(g1), _p(g2), _p(ids), int(ids.dtype == torch.int64), ids.numel(), D, int(skip_id), _p(dtable), _stream()), "fs2k_scatter_add_rows")
+    _count()
+    return dtable
+
+
+def rows_sum_scatter(drows, g, ids):
+    g = _f32(g, "g")
+    B, L, D = g.shape
+    check(lib().fs2k_rows_sum_scatter(_p(g), _p(_i32(ids)) if ids is not None else None, B, L, D, _p(drows), _stream()), "fs2k_rows_sum_scatter")
+    _count()
+    return drows
+
+
+def aligner_bwd(g_soft, g_logprob, soft, logprob, prior, key_lens, q, k):
+    B, F, C = q.shape
+    T = k.shape[1]
+    dd = torch.empty((B, F, T), dtype=torch.float32, device=q.device)
+    dq, dk = torch.empty_like(q), torch.empty_like(k)
+    gs = _f32(g_soft) if g_soft is not None else None
+    gl = _f32(g_logprob) if g_logprob is not None else None
+    kl = _i32(key_lens) if key_lens is not None else None
+    check(lib().fs2k_aligner_bwd(_p(gs), _p(gl), _p(soft), _p(logprob), _p(prior), _p(kl), _p(q), _p(k), B, F, T, C, _p(dd), _p(dq), _p(dk), _stream()), "fs2k_aligner_bwd")
+    _count(3)
+    return dq, dk

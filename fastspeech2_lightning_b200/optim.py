@@ -1,0 +1,84 @@
+"""Flat-buffer AdamW with fused gradient clipping (and the data-parallel gradient all-reduce).
+
+All trainable parameters are re-pointed into ONE contiguous fp32 buffer and their `.grad`s into a second
+one, so that a training-step tail is: one NCCL all-reduce of the flat gradient (multi-GPU), one Σg²
+reduction, one fused clip + AdamW launch — instead of 400+ per-tensor launches.  Same update rule and
+hyper-parameters as the reference's `torch.optim.AdamW` (fs2/model.py:530-537) with Lightning's
+`gradient_clip_val` (fs2/cli/train.py:38); it is a `torch.optim.Optimizer`, so `NoamLR` and Lightning drive it.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
+                 process_group=None):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("no trainable parameters")
+        if any(not p.is_cuda or p.dtype != torch.float32 for p in params):
+            raise ValueError("FusedAdamW needs fp32 CUDA parameters (no CPU path)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm
+        self.process_group = process_group
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        # 16-byte aligned slices so every parameter keeps vectorised access in the model kernels
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat_p[o: o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[o: o + p.numel()].view_as(p)
+        self._params, self._offs, self.numel = params, offs, n
+        self._step = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Gradients stay views of the flat buffer (never set to None): one memset."""
+        self.flat_g.zero_()
+        for p, o in zip(self._params, self._offs):
+            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
+                p.grad = self.flat_g[o: o + p.numel()].view_as(p)
+
+    def grad_norm(self) -> torch.Tensor:
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib().fs2k_sumsq(self.flat_g.data_ptr(), self.flat_g.numel(), self._sumsq.data_ptr(), stream), "fs2k_sumsq")
+        ops._count()
+        return self._sumsq.sqrt()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        world = 1
+        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(self.process_group)
+            if world > 1:  # data-parallel exchange: one all-reduce of the flat gradient; the mean folds into the update
+                torch.distributed.all_reduce(self.flat_g, group=self.process_group)
+        g = self.param_groups[0]
+        self._step += 1
+        stream = torch.cuda.current_stream().cuda_stream
+        sumsq = None
+        if self.max_grad_norm is not None:
+            check(lib().fs2k_sumsq(self.flat_g.data_ptr(), self.flat_g.numel(), self._sumsq.data_ptr(), stream), "fs2k_sumsq")
+            ops._count()
+            sumsq = self._sumsq.data_ptr()
+        check(lib().fs2k_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                    self.flat_p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                    float(g["weight_decay"]), self._step, float(self.max_grad_norm or 0.0), 1.0 / world, sumsq, stream),
+              "fs2k_adamw_step")
+        ops._count()
+        return loss

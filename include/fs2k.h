@@ -138,9 +138,10 @@ int fs2k_rowdot(const float* x, const float* w, const float* b, const uint8_t* m
 int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
 
 /* ---- attention (torchaudio conformer.py:151-153,193-202) ------------------------------------------
- * qkv [B,L,3·H·hd] packed in_proj output; out [B,L,H·hd]; keys >= lens[b] masked; lse_out optional [B,H,L]. */
-int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float* out,
-                       float* lse_out, fs2k_stream_t stream);
+ * qkv [B,L,3·H·hd] packed in_proj output; out [B,L,H·hd]; keys >= lens[b] masked; lse_out optional [B,H,L];
+ * dropout_p > 0 (training): dropout on the attention probabilities, mask = counter hash of (seed, b, h, q, k). */
+int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float dropout_p, long seed,
+                       float* out, float* lse_out, fs2k_stream_t stream);
 
 /* ---- depthwise conv (conformer.py:50-65 with GLU/BatchNorm/SiLU fused; fs2/blocks.py:8-15) ---------
  * x [B,L,ldx] (glu: value c, gate c+C); w [C][K]; scale/shift non-NULL: y = silu((conv+bias)*scale+shift). */
@@ -166,10 +167,66 @@ int fs2k_bin_loss_fwd(const float* hard, const float* soft, long N, float eps, d
 int fs2k_bin_loss_bwd(const float* hard, const float* soft, long N, float eps, const double* sums, const float* gout,
                       float* dsoft, fs2k_stream_t stream);
 
+/* ---- backward kernels (training step: fs2/model.py:384-390 + Lightning's backward) ----------------------
+ * Every forward entry point above has its gradient here; torch.autograd only sequences the calls.
+ * act_bwd:  gz = g · row_mask · alpha · act'(·); mode 0 none, 1 relu (aux = output), 2 silu (aux = pre-activation),
+ *           3 tanh (aux = output).           colsum: out[c] = Σ_m z[m,c] (bias gradients).
+ * repack_weight_t: [taps][N][K] → [taps][K][N] with reversed taps (weights of the transposed conv, so dx is a
+ *           forward fs2k_gemm_* call on gz).  unpack_conv_weight: [taps][N][K] → PyTorch [N][K][taps].
+ * gemm_wgrad: dW[tap][n][k] = Σ_(b,l) G[b,l,n] · X[b,l+tap-pad,k]  (dW zeroed here, split over rows + atomics). */
+int fs2k_act_bwd(const float* g, const float* aux, int mode, float alpha, const uint8_t* row_mask, long M, int C,
+                 float* gz, fs2k_stream_t stream);
+int fs2k_colsum(const float* z, long M, int C, float* out, fs2k_stream_t stream);
+int fs2k_repack_weight_t(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
+int fs2k_unpack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
+int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
+                    float* dW, fs2k_stream_t stream);
+/* LayerNorm backward (dgamma/dbeta zeroed here, accumulated with atomics) */
+int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       long M, int D, float* dx, float* dgamma, float* dbeta, fs2k_stream_t stream);
+/* BatchNorm1d (+ activation) backward: y = act(z*scale + shift), zhat = (z - mean)*rstd.
+ * training: gz = scale*(gu - mean(gu) - zhat*mean(gu*zhat)); eval: gz = gu*scale; dgamma = Σ gu*zhat, dbeta = Σ gu.
+ * sums: 2C doubles of scratch. */
+int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift, const float* mean,
+                    const float* rstd, int act, int training, long M, int C, double* sums, float* gz, float* dgamma,
+                    float* dbeta, fs2k_stream_t stream);
+/* attention backward (flash style, recomputes P from lse); delta: [B,H,L] scratch; dqkv [B,L,3·H·hd] */
+int fs2k_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, const int* lens,
+                           int B, int L, int H, int head_dim, float dropout_p, long seed, float* delta, float* dqkv,
+                           fs2k_stream_t stream);
+/* depthwise conv backward (glu: x = (value, gate) and dx has the same 2C layout); dw/dbias zeroed here */
+int fs2k_dwconv_bwd(const float* gz, const float* x, int ldx, int B, int L, int C, const float* w, int K, int glu,
+                    float* dx, float* dw, float* dbias, fs2k_stream_t stream);
+int fs2k_rowdot_bwd(const float* g, const float* x, const float* w, const uint8_t* mask, long M, int D, float* dx,
+                    float* dw, float* db, fs2k_stream_t stream);
+/* LengthRegulator backward: contiguous segment sums of the two output gradients (either may be NULL) */
+int fs2k_lr_bwd(const float* g_out, const float* g_out_pos, const int* cum, int B, int T, int D, int F, float* dx,
+                fs2k_stream_t stream);
+/* dtable[ids[n],:] += g1[n,:] (+ g2[n,:]), rows with id == skip_id skipped (padding_idx); dtable NOT zeroed */
+int fs2k_scatter_add_rows(const float* g1, const float* g2, const void* ids, int ids_are_int64, long N, int D,
+                          long skip_id, float* dtable, fs2k_stream_t stream);
+/* drows[ids ? ids[b] : b, :] += Σ_l g[b,l,:]  (speaker / language / style rows); drows NOT zeroed */
+int fs2k_rows_sum_scatter(const float* g, const int* ids, int B, int L, int D, float* drows, fs2k_stream_t stream);
+/* aligner backward: gradients w.r.t. the projected queries/keys from g_soft and/or g_logprob; dd [B,F,T] scratch */
+int fs2k_aligner_bwd(const float* g_soft, const float* g_logprob, const float* soft, const float* logprob,
+                     const float* prior, const int* key_lens, const float* q, const float* k, int B, int F, int T,
+                     int C, float* dd, float* dq, float* dk, fs2k_stream_t stream);
+
+/* ---- optimizer over one flat buffer (torch.optim.AdamW at fs2/model.py:530-537; clip 1.0 at fs2/cli/train.py:38) ---
+ * sumsq: out[0] = Σ g² (fp64).  adamw_step: g' = g·grad_scale·min(1, max_norm/(‖g·grad_scale‖+1e-6)) when sumsq is given
+ * (grad_scale = 1/world_size folds the data-parallel mean), then AdamW with decoupled weight decay and bias correction
+ * for `step` (1-based). */
+int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t stream);
+int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, long step, float max_norm, float grad_scale, const double* sumsq,
+                    fs2k_stream_t stream);
+
 /* ---- small elementwise helpers ------------------------------------------------------------------------ */
 int fs2k_axpby(const float* a, float alpha, const float* b, float beta, long N, float* out, fs2k_stream_t stream);
 int fs2k_gather_rows(const float* table, const long long* ids, long R, int D, float* out, fs2k_stream_t stream);
 int fs2k_tanh(const float* x, long N, float* y, fs2k_stream_t stream);
+/* dropout: y = x·keep/(1-p), keep from a counter hash of (seed, index); the backward calls it again on the gradient */
+int fs2k_dropout(const float* x, float p, long seed, long N, float* y, fs2k_stream_t stream);
 
 #ifdef __cplusplus
 }
