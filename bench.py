@@ -260,6 +260,7 @@ def run_ours(args, wl_name, wl, rank, world, device):
         "clocks": clk.summary(),
         "roofline": roof,
         "step_flops": flops_fwd(B, T, F), "step_tflops": flops_fwd(B, T, F) / (ms_dev / args.steps * 1e-3) / 1e12,
+        "gpu_busy_ms_per_step": tot_ms / 2,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, cfg, host_batches[0])
@@ -388,6 +389,7 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e / args.steps, "api": "FastSpeech2.training_step + FusedAdamW.step"},
         "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roof,
         "step_flops": step_flops, "step_tflops": step_flops / (ms_dev / args.steps * 1e-3) / 1e12,
+        "gpu_busy_ms_per_step": tot_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, secs, cores = cpu_train_baseline(wl, steps=1)
@@ -571,7 +573,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="synth_c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="train_c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--also", default="synth_c1,mas_c2", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
@@ -595,6 +598,17 @@ def main():
 
     _ops.set_precision(args.precision)
     line = run_ours(args, args.workload, wl, rank, world, device)
+    if world == 1 and args.also:
+        # the other two headline numbers of BASELINE.json's metric (mel frames/s synthesized, MAS ms/batch)
+        import copy
+
+        line["also"] = {}
+        for name in [n for n in args.also.split(",") if n and n != args.workload]:
+            a2 = copy.copy(args)
+            a2.no_cpu_baseline = True
+            a2.steps = min(args.steps, 10)
+            sub = run_ours(a2, name, WORKLOADS[name], rank, world, device)
+            line["also"][name] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "config") if k in sub}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
