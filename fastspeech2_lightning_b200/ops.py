@@ -551,6 +551,15 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool):
     else:
         B, L = g.shape[0], g.shape[1]
     N, K = g.shape[-1], x.shape[-1]
+    if PRECISION != "fp32" and B * L > 0 and lib().fs2k_gemm_wgrad_tc_supported(N, K, N, K):
+        # tensor cores (tcgen05, MN-major operands); the kernel writes the parameter layout directly
+        ws_bytes = lib().fs2k_gemm_wgrad_tc_workspace_bytes(B, L, N, K, taps)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+        out = torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
+        check(lib().fs2k_gemm_wgrad_tc(_p(g), N, _p(x), K, B, L, N, K, taps, pad, 3 if PRECISION == "tf32x3" else 1,
+                                       _p(ws), ws_bytes, _p(out), _stream()), "fs2k_gemm_wgrad_tc")
+        _count(2)
+        return out
     dw = torch.empty((taps, N, K), dtype=torch.float32, device=g.device)
     check(lib().fs2k_gemm_wgrad(_p(g), N, _p(x), K, B, L, N, K, taps, pad, _p(dw), _stream()), "fs2k_gemm_wgrad")
     _count()

@@ -181,6 +181,14 @@ int fs2k_repack_weight_t(const float* w, int N, int K, int taps, float* out, fs2
 int fs2k_unpack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
 int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
                     float* dW, fs2k_stream_t stream);
+/* Tensor-core weight gradient (gemm_wgrad_tc.cu): both operands MN-major for tcgen05.mma (the contraction runs over
+ * rows), row range split over CTAs, partial tiles summed in a fixed order (deterministic); the result is written
+ * in the PARAMETER layout: [N][K][taps] (Conv1d) — identical to [N][K] when taps == 1.  Needs N % 128 == 0 and
+ * K % 32 == 0 (K % 256 == 0 when K >= 256); other shapes use fs2k_gemm_wgrad. */
+int fs2k_gemm_wgrad_tc_supported(int N, int K, int ldg, int ldx);
+size_t fs2k_gemm_wgrad_tc_workspace_bytes(int B, int L, int N, int K, int taps);
+int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
+                       int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout, fs2k_stream_t stream);
 /* LayerNorm backward (dgamma/dbeta zeroed here, accumulated with atomics) */
 int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                        long M, int D, float* dx, float* dgamma, float* dbeta, fs2k_stream_t stream);
