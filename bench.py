@@ -578,6 +578,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--backward-precision", default=None, choices=["fp32", "tf32", "tf32x3"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -596,7 +597,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=device)
     from fastspeech2_lightning_b200 import ops as _ops
 
-    _ops.set_precision(args.precision)
+    _ops.set_precision(args.precision, args.backward_precision)
     line = run_ours(args, args.workload, wl, rank, world, device)
     if world == 1 and args.also:
         # the other two headline numbers of BASELINE.json's metric (mel frames/s synthesized, MAS ms/batch)

@@ -66,10 +66,11 @@ def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b):
     dx = dw = db = None
     if needs_b:
         db = ops.colsum(g)
-    if needs_x:
-        dx = ops.gemm(g, ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
-    if needs_w:
-        dw = ops.gemm_wgrad(g, x, taps, pad, conv_layout)
+    with ops.backward_precision():
+        if needs_x:
+            dx = ops.gemm(g, ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
+        if needs_w:
+            dw = ops.gemm_wgrad(g, x, taps, pad, conv_layout)
     return dx, dw, db
 
 

@@ -277,11 +277,31 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
 PRECISION = "tf32x3"
 
 
-def set_precision(mode: str) -> None:
-    global PRECISION
-    if mode not in ("fp32", "tf32", "tf32x3"):
-        raise ValueError(mode)
+# Arithmetic of the gradient contractions (dgrad / wgrad); None = same as PRECISION.
+BACKWARD_PRECISION = None
+
+
+def set_precision(mode: str, backward: str | None = None) -> None:
+    global PRECISION, BACKWARD_PRECISION
+    for m in (mode, backward):
+        if m not in (None, "fp32", "tf32", "tf32x3"):
+            raise ValueError(m)
     PRECISION = mode
+    BACKWARD_PRECISION = backward
+
+
+class backward_precision:
+    """Context used by the autograd Functions: run the enclosed contractions in BACKWARD_PRECISION."""
+
+    def __enter__(self):
+        global PRECISION
+        self.prev = PRECISION
+        if BACKWARD_PRECISION is not None:
+            PRECISION = BACKWARD_PRECISION
+
+    def __exit__(self, *a):
+        global PRECISION
+        PRECISION = self.prev
 
 
 def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,

@@ -128,6 +128,8 @@ int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const float* W, 
  * the normalised row is wanted.  fs2k_gemm_tc_supported: K % 4 == 0, lda % 4 == 0, N % 16 == 0 (N <= 256)
  * or N % 128 == 0. */
 int fs2k_gemm_tc_supported(int K, int N, int lda, int taps);
+/* profiling aid: 8 uint64 globaltimer stamps of CTA (0,0) of subsequent fs2k_gemm_tc launches (NULL switches it off) */
+int fs2k_gemm_tc_set_debug_stamps(void* device_buffer);
 int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
                  const float* bias, const float* scale, const float* shift, int act, float alpha,
                  const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, const float* ln_gamma,

@@ -1,5 +1,6 @@
-"""Two eager synthesis steps of the C1 workload (first = warm-up) — the command the ncu captures wrap.
-usage: python profiles/one_step.py [precision] ; prints the number of kernel launches per step."""
+"""Two eager steps of a bench workload (first = warm-up) — the command the ncu captures wrap.
+usage: python profiles/one_step.py [precision] [workload]   (workload: synth_c1 | synth_c4 | train_c2)
+prints the number of kernel launches per step."""
 import sys
 from pathlib import Path
 
@@ -10,14 +11,32 @@ import bench
 from fastspeech2_lightning_b200 import ops, synthetic
 
 ops.set_precision(sys.argv[1] if len(sys.argv) > 1 else "tf32x3")
-wl = bench.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "synth_c1"]
+name = sys.argv[2] if len(sys.argv) > 2 else "synth_c1"
+wl = bench.WORKLOADS[name]
 dev = torch.device("cuda:0")
-cfg, model = bench.build_model(wl, dev)
-batch = synthetic.batch_to(bench.make_batches(wl, 1, 0)[0], dev)
-with torch.no_grad():
-    model(batch, inference=True)
-    torch.cuda.synchronize()
-    n0 = ops.launch_count
-    model(batch, inference=True)
-    torch.cuda.synchronize()
+if wl["kind"] == "train":
+    cfg, model = bench.build_train_model(dev)
+    (opt,), (sched,) = model.configure_optimizers()
+    batch = synthetic.batch_to(bench.make_train_batches(wl, 1, 0)[0], dev)
+
+    def step():
+        opt.zero_grad()
+        out = model(batch)
+        model.loss(out, batch, 0)["total"].backward()
+        opt.step()
+else:
+    cfg, model = bench.build_model(wl, dev)
+    batch = synthetic.batch_to(bench.make_batches(wl, 1, 0)[0], dev)
+
+    def step():
+        with torch.no_grad():
+            model(batch, inference=True)
+
+step()
+torch.cuda.synchronize()
+n0 = ops.launch_count
+torch.cuda.cudart().cudaProfilerStart()
+step()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print("launches_per_step", ops.launch_count - n0, "first_step", n0)

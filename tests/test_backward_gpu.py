@@ -216,8 +216,13 @@ def test_aligner_backward():
     check_grads([soft[:, 0], logprob[:, 0]], [soft_ref, lp], l, r, what="aligner")
 
 
+@pytest.mark.parametrize("bwd", [None])  # single-pass TF32 gradients drift to ~1e-2 in the first layers: not used
 @pytest.mark.parametrize("name", ["train_bn", "train_frame_level"])
-def test_training_step_gradients_match_reference(name):
+def test_training_step_gradients_match_reference(name, bwd, request):
+    from fastspeech2_lightning_b200 import ops
+
+    ops.set_precision("tf32x3", bwd)
+    request.addfinalizer(lambda: ops.set_precision("tf32x3", None))
     meta, gold = load_case(name)
     model = build_model(meta)
     batch = case_batch(meta, DEV)
@@ -239,11 +244,12 @@ def test_training_step_gradients_match_reference(name):
             continue
         rel = abs(float(gr.norm()) - norm) / max(norm, 1e-6)
         worst = max(worst, rel)
-        assert rel <= 2e-3, f"{n}: |grad| {float(gr.norm()):.6e} vs reference {norm:.6e}"
+        print(f"  {rel:.2e} {n}") if rel > 1e-3 else None
+        assert rel <= (2e-3 if bwd is None else 1e-2), f"{n}: |grad| {float(gr.norm()):.6e} vs reference {norm:.6e}"
         h = torch.zeros(16, dtype=torch.float64)
         h[: min(16, gr.numel())] = gr[:16]
         scale = max(float(np.abs(head).max()), norm / max(gr.numel(), 1) ** 0.5, 1e-9)
-        assert float((h - torch.from_numpy(head).double()).abs().max()) <= 5e-3 * scale + 1e-7, n
+        assert float((h - torch.from_numpy(head).double()).abs().max()) <= (5e-3 if bwd is None else 3e-2) * scale + 1e-7, n
     for k, want in gold.items():
         if k.startswith("bn."):
             close(model.state_dict()[k[3:]], want, 1e-4, k)
