@@ -106,6 +106,7 @@ class VarianceAdaptor(nn.Module):
                                            align_query_enc_type="3xconv")
         # Σ duration == mel_len sanity check needs a host read (BadDataError, :289-304); benchmarks may turn it off
         self.validate_durations = True
+        self.last_bucket_ids: dict = {}
 
     # ------------------------------------------------------------------------------------------
     def binarize_attention(self, attn, in_lens, out_lens):
@@ -131,6 +132,8 @@ class VarianceAdaptor(nn.Module):
             y, ids = fns.bucketize_embed_add(target, 1.0, bins, embedding.weight, x)
         else:
             y, ids, prediction = fns.bucketize_embed_add(prediction, float(control), bins, embedding.weight, x, return_scaled=True)
+        # kept for stage-wise parity checks (the ids are a discrete function of fp32 values)
+        self.last_bucket_ids["pitch" if embedding is self.pitch_embedding else "energy"] = ids
         return prediction, y, ids
 
     def average_variance(self, var, durs):

@@ -286,9 +286,11 @@ def gst_style_encoder(speech, sd, training=False, p="gst"):
 # ---------------------------------------------------------------------------------------
 # full forward — fs2/model.py:153-268 with VarianceAdaptor.forward fs2/variance_adaptor.py:224-412
 # ---------------------------------------------------------------------------------------
-def forward(sd, cfg: Cfg, batch, stats_bins=None, inference=False, control=(1.0, 1.0, 1.0), training=False, new_stats=None):
+def forward(sd, cfg: Cfg, batch, stats_bins=None, inference=False, control=(1.0, 1.0, 1.0), training=False, new_stats=None,
+            inject=None):
     """Returns the reference's 16-key output dict (+ `va_output`, `enc_output` for stage-wise checks).
-    `control` = (pitch, energy, duration).  `training` selects BatchNorm batch statistics."""
+    `control` = (pitch, energy, duration).  `training` selects BatchNorm batch statistics.
+    `inject={"attn_hard": t}` replaces the MAS result (stage-wise parity: discrete decisions fed in)."""
     teacher_forcing = bool(inference and batch["mel_lens"] is not None)  # model.py:162-165
     src_lens = batch["src_lens"]
     T = int(batch["max_src_len"])
@@ -328,6 +330,8 @@ def forward(sd, cfg: Cfg, batch, stats_bins=None, inference=False, control=(1.0,
     if (teacher_forcing or not inference) and cfg.learn_alignment:  # :248-305
         attn_soft, attn_logprob = conv_attention(batch["mel"], inputs, src_mask, batch["duration"], sd)
         attn_hard = binarize_attention(attn_soft, src_lens, mel_lens)
+        if inject and "attn_hard" in inject:
+            own_attn_hard, attn_hard = attn_hard, inject["attn_hard"]
         duration_target = attn_hard.sum(2)[:, 0, :].int()
         if energy_target is not None and cfg.energy_level == "phone":
             energy_target = average_variance(energy_target, duration_target)
@@ -343,8 +347,12 @@ def forward(sd, cfg: Cfg, batch, stats_bins=None, inference=False, control=(1.0,
         else:
             pred = pred * ctl
             ids = torch.bucketize(pred, bins)
+        own_ids[name] = ids
+        if inject and "bucket_ids" in inject:  # discrete decision fed in (stage-wise parity)
+            ids = inject["bucket_ids"][name]
         return pred, F.embedding(ids, sd[f"{va}.{name}_embedding.weight"]), ids
 
+    own_ids = {}
     energy_prediction = pitch_prediction = None
     ids_out = {}
     if cfg.energy_level == "phone":  # :309-329
@@ -398,6 +406,7 @@ def forward(sd, cfg: Cfg, batch, stats_bins=None, inference=False, control=(1.0,
         "va_output": va_output,
         "text_emb": inputs,
         "bucket_ids": ids_out,
+        "own_bucket_ids": own_ids,
         "duration_rounded": duration_rounded,
     }
 
