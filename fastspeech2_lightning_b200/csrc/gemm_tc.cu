@@ -95,10 +95,11 @@ constexpr int TC_ROWS_PER_ITER = 4;             // rows a warp keeps in flight i
 template <int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, TcEpilogue ep) {
+               int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
+               TcEpilogue ep) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int TC_STAGES = TcStages<PASSES>::value;
-    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_split[TC_STAGES], s_tmem_full;
+    const int TC_STAGES = n_stages;  // 2..4, as many as fit next to the staging tile (host decides)
+    __shared__ __align__(8) uint64_t s_full[4], s_empty[4], s_split[4], s_tmem_full;
     __shared__ uint32_t s_tmem_base;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -339,6 +340,8 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     FS2K_REQUIRE(!scale || shift, FS2K_ERR_NULL);
     FS2K_REQUIRE((ldc & 3) == 0 && (!residual || (ldr & 3) == 0), FS2K_ERR_UNSUPPORTED);
     int block_n = N <= 256 ? N : ((N % 256) == 0 ? 256 : 128);
+    // (measured: narrowing 3×TF32 tiles to 128 columns for a 3-stage ring shortens the main loop 11 → 7.6 µs per tile
+    // but doubles the number of ≈5 µs epilogues — slower overall on these 1-wave problems, so tiles stay 256 wide)
     if (!ln_out) {
         // small-M problems (encoder, predictors: ≤ 20 row tiles) are latency-bound per CTA: narrow the
         // column tile until the grid covers most of the 148 SMs
@@ -381,7 +384,10 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     TcEpilogue ep{bias, scale, shift, act, alpha, residual, ldr, row_mask, C, ldc,
                   ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out, g_tc_debug_stamps};
     const size_t stage = (size_t)(TC_BM + block_n) * TC_BK * 4 * (passes == 3 ? 2 : 1);
-    size_t smem = stage * (passes == 3 ? TcStages<3>::value : TcStages<1>::value);
+    int n_stages = (int)((226 * 1024) / stage);
+    if (n_stages > 4) n_stages = 4;
+    FS2K_REQUIRE(n_stages >= 2, FS2K_ERR_UNSUPPORTED);
+    size_t smem = stage * n_stages;
     const size_t staging = (size_t)TC_BM * (block_n + 4) * 4;
     if (smem < staging) smem = staging;
     smem += 1024;  // manual 1024-byte alignment of the swizzled tiles
@@ -392,11 +398,11 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     if (passes == 3) {
         e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, ep);
+        gemm_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
     } else {
         e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, ep);
+        gemm_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -11,16 +11,31 @@
 // Layout: one CTA per utterance; thread t owns column(s) t + c·blockDim of the current row
 // (`prev[c]` lives in a register), the left neighbour comes from `__shfl_up` and, across warp
 // and chunk boundaries, from a double-buffered shared-memory word; one `__syncthreads` per mel
-// frame.  Rows are prefetched PF frames ahead in registers.  The backtrack is done by warp 0,
-// 32 frames per step: lane r fetches the two direction words that can hold frame (top−r)'s
-// column, then the dependent chain runs through shuffles only.
+// frame.  The DP is latency bound (F sequential steps), so
+//   * rows are streamed PF frames ahead with `cp.async` into a shared-memory ring: each thread copies
+//     exactly the elements it will read, so completion is tracked per thread with `cp.async.wait_group`
+//     and costs no extra barrier (a register ring does not work: ptxas rotates it with moves that wait on
+//     the load just issued);
+//   * the direction words of DB frames are collected in shared memory and written out in one coalesced
+//     burst, so the per-frame barrier never has a global store in flight.
+// (One column per thread is kept on purpose: four columns per thread was measured 2.5× slower at T = 80 —
+// fewer warps to overlap the `logf` chains — and no faster at T = 1000.)
+// The backtrack is done by warp 0, 32 frames per step: lane r fetches the two direction words that
+// can hold frame (top−r)'s column, then the dependent chain runs through shuffles only.
 #include "common.cuh"
 
 namespace fs2k {
 
-constexpr int kMasPF = 8;  // mel frames kept in flight per thread
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int CHUNKS, bool TAKE_LOG>
+constexpr int MAS_DB = 32;  // frames of direction words buffered in shared memory between flushes
+
+template <int CHUNKS, int PF, bool TAKE_LOG>
 __global__ void __launch_bounds__(1024, 1)
 mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs if TAKE_LOG)
               const int* __restrict__ in_lens,   // [B] text lengths
@@ -30,10 +45,13 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
               int* __restrict__ path,            // [B,F] column of frame f, −1 on padding
               int* __restrict__ durations)       // [B,T]
 {
+    extern __shared__ float ring[];  // [PF][CHUNKS·blockDim] then uint32 sdir[MAS_DB][W]
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
     const int n_mel = min(out_lens[b], F);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int ncols = CHUNKS * blockDim.x;
+    uint32_t* sdir = reinterpret_cast<uint32_t*>(ring + (size_t)PF * ncols);
     const float NEG_INF = -INFINITY;
     __shared__ float bnd[2][CHUNKS * 32];
 
@@ -65,47 +83,51 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
         prev[c] = v;
         if (lane == 31) bnd[0][c * nwarps + warp] = v;
     }
-    // prefetch ring: xr[u][c] holds row (i0+u)
-    float xr[kMasPF][CHUNKS];
+    auto issue = [&](int r) {  // stream row r into ring slot r % PF (one commit group per row, even when empty)
+        if (r < n_mel) {
+            float* slot = ring + (size_t)(r % PF) * ncols;
 #pragma unroll
-    for (int u = 0; u < kMasPF; ++u)
-#pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-            int r = 1 + u;
-            xr[u][c] = (live[c] && r < n_mel) ? x[(size_t)r * T + col[c]] : 0.f;
+            for (int c = 0; c < CHUNKS; ++c)
+                if (live[c]) cp_async4(slot + c * blockDim.x + tid, x + (size_t)r * T + col[c]);
         }
+        cp_async_commit();
+    };
+    for (int r = 1; r <= PF; ++r) issue(r);
     __syncthreads();
 
-    for (int i0 = 1; i0 < n_mel; i0 += kMasPF) {
+    for (int i = 1; i < n_mel; ++i) {
+        cp_async_wait<PF - 1>();  // this thread's copies of row i have landed
+        const float* slot = ring + (size_t)(i % PF) * ncols;
+        const int par = (i - 1) & 1;
+        uint32_t* drow = sdir + (size_t)((i - 1) % MAS_DB) * W;
 #pragma unroll
-        for (int u = 0; u < kMasPF; ++u) {
-            const int i = i0 + u;
-            if (i >= n_mel) break;  // block-uniform
-            const int par = (i - 1) & 1;
-#pragma unroll
-            for (int c = 0; c < CHUNKS; ++c) {
-                float xv = xr[u][c];
-                {   // refill this ring slot with row i+PF
-                    int r = i + kMasPF;
-                    xr[u][c] = (live[c] && r < n_mel) ? x[(size_t)r * T + col[c]] : 0.f;
-                }
-                if (TAKE_LOG) xv = logf(xv);
-                float left = __shfl_up_sync(0xffffffffu, prev[c], 1);
-                const int g = c * nwarps + warp;  // global warp slot == direction word index
-                if (lane == 0) left = (g == 0) ? NEG_INF : bnd[par][g - 1];
-                const float up = prev[c];
-                // backtrack predicate of alignment.py:68 evaluated for cell (i, col); column 0 never moves
-                const bool diag = (left >= up) && (col[c] >= 1);
-                const uint32_t word = __ballot_sync(0xffffffffu, diag && live[c]);
-                if (lane == 0 && g < W) d[(size_t)i * W + g] = word;
-                const float m = up > left ? up : left;  // max(prev_log1, prev_log2), alignment.py:59
-                const float cur = live[c] ? __fadd_rn(xv, m) : NEG_INF;
-                prev[c] = cur;
-                if (lane == 31) bnd[par ^ 1][g] = cur;
-            }
-            __syncthreads();
+        for (int c = 0; c < CHUNKS; ++c) {
+            float xv = live[c] ? slot[c * blockDim.x + tid] : 0.f;
+            if (TAKE_LOG) xv = logf(xv);
+            float left = __shfl_up_sync(0xffffffffu, prev[c], 1);
+            const int g = c * nwarps + warp;  // global warp slot == direction word index
+            if (lane == 0) left = (g == 0) ? NEG_INF : bnd[par][g - 1];
+            const float up = prev[c];
+            // backtrack predicate of alignment.py:68 evaluated for cell (i, col); column 0 never moves
+            const bool diag = (left >= up) && (col[c] >= 1);
+            const uint32_t word = __ballot_sync(0xffffffffu, diag && live[c]);
+            if (lane == 0 && g < W) drow[g] = word;
+            const float m = up > left ? up : left;  // max(prev_log1, prev_log2), alignment.py:59
+            const float cur = live[c] ? __fadd_rn(xv, m) : NEG_INF;
+            prev[c] = cur;
+            if (lane == 31) bnd[par ^ 1][g] = cur;
+        }
+        issue(i + PF);  // the slot just consumed is refilled PF frames ahead
+        __syncthreads();
+        // flush the buffered direction words of frames (i−n+1 … i) with coalesced stores
+        const int n_buf = ((i - 1) % MAS_DB) + 1;
+        if (n_buf == MAS_DB || i == n_mel - 1) {
+            const int first = i - n_buf + 1;
+            for (int e = tid; e < n_buf * W; e += blockDim.x) d[(size_t)first * W + e] = sdir[e];
+            __syncthreads();  // sdir is rewritten by the next frame
         }
     }
+    cp_async_wait<0>();
 
     // ---- backtrack (alignment.py:62-73), warp 0, 32 frames per step ----
     if (warp == 0) {
@@ -139,6 +161,19 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
     for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
 }
 
+// log of the soft alignment (the `torch.log(attn.data)` of variance_adaptor.py:168) as a fully parallel
+// HBM-bound pass, so the sequential DP loop carries no transcendental
+__global__ void __launch_bounds__(256)
+mas_log_kernel(const float* __restrict__ x, long N, float* __restrict__ y) {
+    const long N4 = N >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
+        reinterpret_cast<float4*>(y)[i] = make_float4(logf(v.x), logf(v.y), logf(v.z), logf(v.w));
+    }
+    if (blockIdx.x == 0)
+        for (long i = (N4 << 2) + threadIdx.x; i < N; i += blockDim.x) y[i] = logf(x[i]);
+}
+
 // dense 0/1 map [B,1,F,T] from the per-frame column index: HBM-write bound (4·B·F·T bytes)
 __global__ void __launch_bounds__(256)
 mas_dense_kernel(const int* __restrict__ path, int B, int F, int T, float* __restrict__ hard) {
@@ -159,10 +194,27 @@ mas_dense_kernel(const int* __restrict__ path, int B, int F, int T, float* __res
     }
 }
 
+template <int CHUNKS, int PF, bool LOG>
+static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* attn, const int* in_lens, const int* out_lens,
+                              int F, int T, int W, uint32_t* dirs, int* path, int* durations) {
+    const size_t smem = (size_t)PF * CHUNKS * threads * sizeof(float) + (size_t)MAS_DB * W * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(mas_dp_kernel<CHUNKS, PF, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    mas_dp_kernel<CHUNKS, PF, LOG><<<B, threads, smem, s>>>(attn, in_lens, out_lens, F, T, W, dirs, path, durations);
+    return cudaGetLastError();
+}
+
 }  // namespace fs2k
 
+static size_t mas_dirs_bytes(int B, int F, int T) {
+    const size_t n = (size_t)B * F * ((T + 31) / 32) * sizeof(uint32_t);
+    return (n + 255) / 256 * 256;
+}
+// direction words [B,F,ceil(T/32)] + (for take_log) the log-probabilities [B,F,T]
 extern "C" size_t fs2k_mas_workspace_bytes(int B, int F, int T) {
-    return (size_t)B * F * ((T + 31) / 32) * sizeof(uint32_t);
+    return mas_dirs_bytes(B, F, T) + (size_t)B * F * T * sizeof(float);
 }
 
 extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B,
@@ -179,12 +231,23 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
     const int chunks = (T + threads - 1) / threads;
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t* dirs = (uint32_t*)workspace;
-#define LAUNCH(C, L) mas_dp_kernel<C, L><<<B, threads, 0, s>>>(attn, in_lens, out_lens, F, T, W, dirs, path, durations)
-    if (chunks == 1) { if (take_log) LAUNCH(1, true); else LAUNCH(1, false); }
-    else if (chunks == 2) { if (take_log) LAUNCH(2, true); else LAUNCH(2, false); }
-    else { threads = 1024; if (take_log) LAUNCH(4, true); else LAUNCH(4, false); }
-#undef LAUNCH
-    FS2K_CHECK_LAUNCH();
+    if (take_log) {
+        float* logbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + mas_dirs_bytes(B, F, T));
+        const long n = (long)B * F * T;
+        long g = (n / 4 + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        if (g < 1) g = 1;
+        mas_log_kernel<<<(int)g, 256, 0, s>>>(attn, n, logbuf);
+        FS2K_CHECK_LAUNCH();
+        attn = logbuf;
+    }
+    cudaError_t e;
+#define MAS_ARGS B, threads, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations
+    if (chunks == 1) e = launch_mas<1, 16, false>(MAS_ARGS);
+    else if (chunks == 2) e = launch_mas<2, 16, false>(MAS_ARGS);
+    else { threads = 1024; e = launch_mas<4, 8, false>(MAS_ARGS); }
+#undef MAS_ARGS
+    if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (hard) {
         const long rows = (long)B * F;
         int grid = (int)((rows + 7) / 8);

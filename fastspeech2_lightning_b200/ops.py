@@ -67,7 +67,7 @@ def mas(attn: torch.Tensor, in_lens: torch.Tensor, out_lens: torch.Tensor, take_
     ws_bytes = lib().fs2k_mas_workspace_bytes(B, F, T)
     ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=a.device)
     check(lib().fs2k_mas_fwd(_p(a), int(take_log), _p(il), _p(ol), B, F, T, _p(path), _p(dur), _p(hard), _p(ws), ws_bytes, _stream()), "fs2k_mas_fwd")
-    _count(2 if dense else 1)
+    _count((2 if dense else 1) + (1 if take_log else 0))
     return path, dur, hard
 
 
