@@ -17,46 +17,57 @@ def _d(t):
     return None if t is None else t.detach()
 
 
+def _seed(p) -> int:
+    """A fresh dropout seed from torch's CPU generator (no device sync); 0 when dropout is off."""
+    return int(torch.randint(0, 2**31 - 1, (1,)).item()) if p else 0
+
+
 # ---------------------------------------------------------------------------------------------
 # dropout (Philox-free counter hash: the mask is regenerated from (seed, offset) in backward)
 # ---------------------------------------------------------------------------------------------
 class _Dropout(torch.autograd.Function):
+    """dropout(x) (+ residual) in one launch."""
+
     @staticmethod
-    def forward(ctx, x, p):
-        seed = int(torch.randint(0, 2**31 - 1, (1,)).item())
-        ctx.seed, ctx.p = seed, p
-        return ops.dropout(x, p, seed)
+    def forward(ctx, x, residual, p):
+        seed = _seed(p)
+        ctx.seed, ctx.p, ctx.has_res = seed, p, residual is not None
+        return ops.dropout(x, p, seed, residual)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        return ops.dropout(g.contiguous(), ctx.p, ctx.seed), None
+        g = g.contiguous()
+        return ops.dropout(g, ctx.p, ctx.seed), (g if ctx.has_res else None), None
 
 
-def dropout(x, p: float):
+def dropout(x, p: float, residual=None):
     if not p:
-        return x
-    return _Dropout.apply(x, float(p))
+        return x if residual is None else add(x, residual)
+    return _Dropout.apply(x.contiguous(), residual, float(p))
 
 
 # ---------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
-        y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True)
+    def forward(ctx, x, weight, bias, eps, p):
+        seed = _seed(p)
+        y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True, dropout_p=p, seed=seed)
         ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.drop = (p, seed)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         x, weight, mean, rstd = ctx.saved_tensors
-        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight)
-        return dx, dw, db, None
+        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight, *ctx.drop)
+        return dx, dw, db, None, None
 
 
 def layernorm(x, weight, bias, eps, dropout_p=0.0):
-    return dropout(_LayerNorm.apply(x.contiguous(), weight, bias, eps), dropout_p)
+    """LayerNorm with the following Dropout fused into the same launch (forward and backward)."""
+    return _LayerNorm.apply(x.contiguous(), weight, bias, eps, float(dropout_p))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -78,16 +89,20 @@ class _Gemm(torch.autograd.Function):
     """y = act(conv(x, W) + b)·alpha + residual   (Linear when W is 2-D)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, act, alpha):
+    def forward(ctx, x, weight, bias, residual, act, alpha, p=0.0):
         conv_layout = weight.dim() == 3
         w_taps = ops.conv_weight_taps(weight) if conv_layout else weight.reshape(1, *weight.shape)
         pad = (w_taps.shape[0] - 1) // 2
         aux = None
-        if act == "silu":  # keep the pre-activation for silu'
+        seed = _seed(p)
+        ctx.drop = (p, seed)
+        if act == "silu":  # keep the pre-activation for silu'; SiLU (+ Dropout) in one elementwise launch
             aux = ops.gemm(x, w_taps, bias, taps_pad=pad)
-            y = ops.affine_act(aux, None, None, "silu", residual)
+            y = ops.affine_act(aux, None, None, "silu", residual, dropout_p=p, seed=seed)
             if alpha != 1.0:
                 raise NotImplementedError("alpha with silu")
+        elif p:
+            raise NotImplementedError("fused dropout is only wired for the SiLU epilogue")
         else:
             y = ops.gemm(x, w_taps, bias, taps_pad=pad, act=act, alpha=alpha, residual=residual)
             if act in ("relu", "tanh"):
@@ -104,22 +119,24 @@ class _Gemm(torch.autograd.Function):
         x, w_taps, aux = ctx.saved_tensors
         act, alpha, pad, conv_layout, has_bias, has_res = ctx.meta
         g = g.contiguous()
-        gz = g if (act is None and alpha == 1.0) else ops.act_bwd(g, aux, act, alpha)
+        gz = g if (act is None and alpha == 1.0) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                     has_bias and ctx.needs_input_grad[2])
-        return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None
+        return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None, None
 
 
 def linear(x, weight, bias, act, alpha, residual, dropout_p=0.0):
-    if residual is not None and dropout_p:
-        # reference order: residual + Dropout(Linear(...)·alpha)
-        y = _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha)
-        return add(dropout(y, dropout_p), residual)
-    return dropout(_Gemm.apply(x.contiguous(), weight, bias, residual, act, alpha), dropout_p)
+    if dropout_p and act == "silu" and residual is None:
+        return _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha, float(dropout_p))
+    if dropout_p:
+        # reference order: residual + Dropout(Linear(...)·alpha): GEMM, then dropout + residual add in one launch
+        y = _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha, 0.0)
+        return dropout(y, dropout_p, residual)
+    return _Gemm.apply(x.contiguous(), weight, bias, residual, act, alpha, 0.0)
 
 
 def conv1d(x, weight, bias, act):
-    return _Gemm.apply(x.contiguous(), weight, bias, None, act, 1.0)
+    return _Gemm.apply(x.contiguous(), weight, bias, None, act, 1.0, 0.0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -127,29 +144,30 @@ class _ConvBnAct(torch.autograd.Function):
     """One PostNet block: Conv1d(k) → BatchNorm1d → act (fs2/layers.py:157-212)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bn_w, bn_b, bn, act, training):
+    def forward(ctx, x, weight, bias, bn_w, bn_b, bn, act, training, p=0.0):
         w_taps = ops.conv_weight_taps(weight)
         pad = (w_taps.shape[0] - 1) // 2
         z = ops.gemm(x, w_taps, bias, taps_pad=pad)
         scale, shift, mean, rstd = ops.bn_scale_shift(bn, z, training, save_stats=True)
-        y = ops.affine_act(z, scale, shift, act)
+        seed = _seed(p)
+        y = ops.affine_act(z, scale, shift, act, None, p, seed)  # BatchNorm affine + act + Dropout in one launch
         ctx.save_for_backward(x, w_taps, z, scale, shift, mean, rstd)
-        ctx.meta = (act, training, pad, bias is not None)
+        ctx.meta = (act, training, pad, bias is not None, p, seed)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         x, w_taps, z, scale, shift, mean, rstd = ctx.saved_tensors
-        act, training, pad, has_bias = ctx.meta
-        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training)
+        act, training, pad, has_bias, p, seed = ctx.meta
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training, p, seed)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, True, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                     has_bias and ctx.needs_input_grad[2])
-        return dx, dw, db, dgamma, dbeta, None, None, None
+        return dx, dw, db, dgamma, dbeta, None, None, None, None
 
 
 def conv1d_bn_act(x, weight, bias, bn, act, training, dropout_p=0.0):
-    return dropout(_ConvBnAct.apply(x.contiguous(), weight, bias, bn.weight, bn.bias, bn, act, training), dropout_p)
+    return _ConvBnAct.apply(x.contiguous(), weight, bias, bn.weight, bn.bias, bn, act, training, float(dropout_p))
 
 
 class _GluDwconvBnSilu(torch.autograd.Function):

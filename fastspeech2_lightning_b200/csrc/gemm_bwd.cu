@@ -13,7 +13,9 @@ namespace fs2k {
 // mode: 0 none, 1 relu (aux = output y), 2 silu (aux = pre-activation z), 3 tanh (aux = output y)
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int mode, float alpha,
-               const uint8_t* __restrict__ row_mask, long M, int C, float* __restrict__ gz) {
+               const uint8_t* __restrict__ row_mask, long M, int C, float drop_p, unsigned long long seed,
+               float* __restrict__ gz) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -21,6 +23,10 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
         float s = alpha;
         if (row_mask) s *= row_mask[i / C4] ? 1.f : 0.f;
         float o[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+        if (drop_p > 0.f) {  // the forward applied dropout after the activation: same mask on the gradient
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? o[k] * inv_keep : 0.f;
+        }
         if (mode != 0) {
             const float4 a = reinterpret_cast<const float4*>(aux)[i];
             const float av[4] = {a.x, a.y, a.z, a.w};
@@ -160,12 +166,12 @@ static inline int ew_grid2(long n) {
 }
 
 extern "C" int fs2k_act_bwd(const float* g, const float* aux, int mode, float alpha, const uint8_t* row_mask, long M,
-                            int C, float* gz, fs2k_stream_t stream) {
+                            int C, float dropout_p, long seed, float* gz, fs2k_stream_t stream) {
     FS2K_REQUIRE(M >= 0 && C > 0 && mode >= 0 && mode <= 3, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
     if (M == 0) return FS2K_OK;
     FS2K_REQUIRE(g && gz && (mode == 0 || aux), FS2K_ERR_NULL);
-    act_bwd_kernel<<<ew_grid2(M * (C >> 2)), 256, 0, (cudaStream_t)stream>>>(g, aux, mode, alpha, row_mask, M, C, gz);
+    act_bwd_kernel<<<ew_grid2(M * (C >> 2)), 256, 0, (cudaStream_t)stream>>>(g, aux, mode, alpha, row_mask, M, C, dropout_p, (unsigned long long)seed, gz);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -12,8 +12,9 @@ namespace fs2k {
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, long M, int D, float* __restrict__ y, float* __restrict__ mean_out,
-                 float* __restrict__ rstd_out) {
+                 float eps, long M, int D, float drop_p, unsigned long long seed, float* __restrict__ y,
+                 float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int lane = threadIdx.x & 31;
     const int D4 = D >> 2;
     for (long m = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M;
@@ -55,6 +56,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                 o.y = (v[i].y - mean) * rstd * g.y + b.y;
                 o.z = (v[i].z - mean) * rstd * g.z + b.z;
                 o.w = (v[i].w - mean) * rstd * g.w + b.w;
+                if (drop_p > 0.f) {
+                    const unsigned long long e = (unsigned long long)m * D + q * 4;
+                    o.x = hash_uniform(seed, e) >= drop_p ? o.x * inv_keep : 0.f;
+                    o.y = hash_uniform(seed, e + 1) >= drop_p ? o.y * inv_keep : 0.f;
+                    o.z = hash_uniform(seed, e + 2) >= drop_p ? o.z * inv_keep : 0.f;
+                    o.w = hash_uniform(seed, e + 3) >= drop_p ? o.w * inv_keep : 0.f;
+                }
                 yr[q] = o;
             }
         }
@@ -141,7 +149,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long M, int 
 // y = act(z·scale[c] + shift[c]) (+ residual)    act: 0 none, 1 relu, 2 silu, 3 tanh
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                  int act, const float* __restrict__ residual, long M, int C, float* __restrict__ y) {
+                  int act, const float* __restrict__ residual, long M, int C, float drop_p, unsigned long long seed,
+                  float* __restrict__ y) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -155,6 +165,7 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
             if (act == 1) o[k] = fmaxf(o[k], 0.f);
             else if (act == 2) o[k] = silu(o[k]);
             else if (act == 3) o[k] = tanhf(o[k]);
+            if (drop_p > 0.f) o[k] = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? o[k] * inv_keep : 0.f;
         }
         if (residual) {
             const float4 r = reinterpret_cast<const float4*>(residual)[i];
@@ -169,7 +180,9 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
 using namespace fs2k;
 
 extern "C" int fs2k_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, long M, int D,
-                                  float* y, float* mean_out, float* rstd_out, fs2k_stream_t stream) {
+                                  float dropout_p, long seed, float* y, float* mean_out, float* rstd_out,
+                                  fs2k_stream_t stream) {
+    const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((D & 3) == 0 && D <= 1024, FS2K_ERR_UNSUPPORTED);
     if (M == 0) return FS2K_OK;
@@ -177,9 +190,9 @@ extern "C" int fs2k_layernorm_fwd(const float* x, const float* gamma, const floa
     long g = (M + 7) / 8;
     if (g > 148 * 8) g = 148 * 8;
     cudaStream_t s = (cudaStream_t)stream;
-    if (D <= 256) layernorm_kernel<2><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, y, mean_out, rstd_out);
-    else if (D <= 512) layernorm_kernel<4><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, y, mean_out, rstd_out);
-    else layernorm_kernel<8><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, y, mean_out, rstd_out);
+    if (D <= 256) layernorm_kernel<2><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
+    else if (D <= 512) layernorm_kernel<4><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
+    else layernorm_kernel<8><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -217,14 +230,15 @@ extern "C" int fs2k_bn_finalize(const double* sums, long M, int C, const float* 
 }
 
 extern "C" int fs2k_affine_act(const float* z, const float* scale, const float* shift, int act, const float* residual,
-                               long M, int C, float* y, fs2k_stream_t stream) {
+                               long M, int C, float dropout_p, long seed, float* y, fs2k_stream_t stream) {
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
     if (M == 0) return FS2K_OK;
     FS2K_REQUIRE(z && y && (!scale || shift), FS2K_ERR_NULL);  // scale == NULL: plain activation
     long g = (M * (C >> 2) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    affine_act_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(z, scale, shift, act, residual, M, C, y);
+    affine_act_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(z, scale, shift, act, residual, M, C, dropout_p,
+                                                                (unsigned long long)seed, y);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -7,8 +7,10 @@ namespace fs2k {
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, const float* __restrict__ gamma, long M, int D,
-                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, long M, int D, float drop_p,
+                     unsigned long long seed, float* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ float s_red[8][32 * MAXV * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D4 = D >> 2;
@@ -29,7 +31,14 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
         for (int i = 0; i < MAXV; ++i) {
             const int q = lane + 32 * i;
             if (q < D4) {
-                const float4 gv = reinterpret_cast<const float4*>(g + (size_t)m * D)[q];
+                float4 gv = reinterpret_cast<const float4*>(g + (size_t)m * D)[q];
+                if (drop_p > 0.f) {  // the forward output was dropout(LN(x)): same mask on the incoming gradient
+                    const unsigned long long e = (unsigned long long)m * D + q * 4;
+                    gv.x = hash_uniform(seed, e) >= drop_p ? gv.x * inv_keep : 0.f;
+                    gv.y = hash_uniform(seed, e + 1) >= drop_p ? gv.y * inv_keep : 0.f;
+                    gv.z = hash_uniform(seed, e + 2) >= drop_p ? gv.z * inv_keep : 0.f;
+                    gv.w = hash_uniform(seed, e + 3) >= drop_p ? gv.w * inv_keep : 0.f;
+                }
                 const float4 xv = reinterpret_cast<const float4*>(x + (size_t)m * D)[q];
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 gg[i] = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
@@ -90,7 +99,9 @@ __device__ __forceinline__ float act_grad_from_u(float u, int act) {
 __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    int act, long M, int C, long rows_per_cta, double* __restrict__ sums) {
+                    int act, long M, int C, long rows_per_cta, float drop_p, unsigned long long seed,
+                    double* __restrict__ sums) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ double s_part[8][128][2];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
@@ -109,7 +120,9 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                 const float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w}, zv[4] = {zv4.x, zv4.y, zv4.z, zv4.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float gu = gv[k] * act_grad_from_u(zv[k] * sc[k] + sh[k], act);
+                    float gk = gv[k];
+                    if (drop_p > 0.f) gk = hash_uniform(seed, (unsigned long long)m * C + c + k) >= drop_p ? gk * inv_keep : 0.f;
+                    const float gu = gk * act_grad_from_u(zv[k] * sc[k] + sh[k], act);
                     s[k] += gu;
                     q[k] += gu * (zv[k] - mu[k]) * rs[k];
                 }
@@ -140,8 +153,10 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const double* __restrict__ sums, int act, int training, long M, int C, float* __restrict__ gz,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    const double* __restrict__ sums, int act, int training, long M, int C, float drop_p,
+                    unsigned long long seed, float* __restrict__ gz, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
     const float inv_m = 1.0f / (float)M;
@@ -159,7 +174,9 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float sc = scale[c + k];
-            const float gu = gv[k] * act_grad_from_u(zv[k] * sc + shift[c + k], act);
+            float gk = gv[k];
+            if (drop_p > 0.f) gk = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? gk * inv_keep : 0.f;
+            const float gu = gk * act_grad_from_u(zv[k] * sc + shift[c + k], act);
             if (training) {
                 const float zh = (zv[k] - mean[c + k]) * rstd[c + k];
                 o[k] = sc * (gu - (float)sums[c + k] * inv_m - zh * (float)sums[C + c + k] * inv_m);
@@ -176,8 +193,9 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 using namespace fs2k;
 
 extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd,
-                                  const float* gamma, long M, int D, float* dx, float* dgamma, float* dbeta,
-                                  fs2k_stream_t stream) {
+                                  const float* gamma, long M, int D, float dropout_p, long seed, float* dx,
+                                  float* dgamma, float* dbeta, fs2k_stream_t stream) {
+    const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((D & 3) == 0 && D <= 1024, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(g && x && mean && rstd && gamma && dx && dgamma && dbeta, FS2K_ERR_NULL);
@@ -189,17 +207,18 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
     long grid = (M + 63) / 64;  // ≥ 8 rows per warp so the per-CTA atomics amortise
     if (grid > 148 * 4) grid = 148 * 4;
     if (grid < 1) grid = 1;
-    if (D <= 256) layernorm_bwd_kernel<2><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dx, dgamma, dbeta);
-    else if (D <= 512) layernorm_bwd_kernel<4><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dx, dgamma, dbeta);
-    else layernorm_bwd_kernel<8><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dx, dgamma, dbeta);
+    if (D <= 256) layernorm_bwd_kernel<2><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    else if (D <= 512) layernorm_bwd_kernel<4><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    else layernorm_bwd_kernel<8><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
 
 extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift,
                                const float* mean, const float* rstd, int act, int training, long M, int C,
-                               double* sums /* [2C] scratch */, float* gz, float* dgamma, float* dbeta,
-                               fs2k_stream_t stream) {
+                               float dropout_p, long seed, double* sums /* [2C] scratch */, float* gz, float* dgamma,
+                               float* dbeta, fs2k_stream_t stream) {
+    const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(g && z && scale && shift && mean && rstd && sums && gz, FS2K_ERR_NULL);
@@ -211,11 +230,11 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     if (ctas > 148 * 4) ctas = 148 * 4;
     const long rows = (M + ctas - 1) / ctas;
     ctas = (M + rows - 1) / rows;
-    bn_bwd_stats_kernel<<<(int)ctas, 256, 0, s>>>(g, z, scale, shift, mean, rstd, act, M, C, rows, sums);
+    bn_bwd_stats_kernel<<<(int)ctas, 256, 0, s>>>(g, z, scale, shift, mean, rstd, act, M, C, rows, dropout_p, useed, sums);
     FS2K_CHECK_LAUNCH();
     long grid = (M * (C >> 2) + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    bn_bwd_apply_kernel<<<(int)grid, 256, 0, s>>>(g, z, scale, shift, mean, rstd, sums, act, training, M, C, gz, dgamma, dbeta);
+    bn_bwd_apply_kernel<<<(int)grid, 256, 0, s>>>(g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, gz, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -6,6 +6,7 @@ current stream.  Nothing here computes with torch ops; there is no CPU path.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -198,14 +199,14 @@ def mask_lens(mask):
 # ---------------------------------------------------------------------------------------------
 # normalisation
 # ---------------------------------------------------------------------------------------------
-def layernorm(x, gamma, beta, eps: float = 1e-5, save_stats: bool = False):
+def layernorm(x, gamma, beta, eps: float = 1e-5, save_stats: bool = False, dropout_p: float = 0.0, seed: int = 0):
     x = _f32(x, "x")
     D = x.shape[-1]
     M = x.numel() // D
     y = torch.empty_like(x)
     mean = torch.empty((M,), dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty((M,), dtype=torch.float32, device=x.device) if save_stats else None
-    check(lib().fs2k_layernorm_fwd(_p(x), _p(_f32(gamma)), _p(_f32(beta)), float(eps), M, D, _p(y), _p(mean), _p(rstd), _stream()), "fs2k_layernorm_fwd")
+    check(lib().fs2k_layernorm_fwd(_p(x), _p(_f32(gamma)), _p(_f32(beta)), float(eps), M, D, float(dropout_p), int(seed), _p(y), _p(mean), _p(rstd), _stream()), "fs2k_layernorm_fwd")
     _count()
     return (y, mean, rstd) if save_stats else y
 
@@ -237,12 +238,12 @@ def bn_scale_shift(bn: torch.nn.modules.batchnorm._BatchNorm, z: Optional[torch.
     return scale, shift
 
 
-def affine_act(z, scale, shift, act=None, residual=None):
+def affine_act(z, scale, shift, act=None, residual=None, dropout_p: float = 0.0, seed: int = 0):
     z = _f32(z, "z")
     C = z.shape[-1]
     M = z.numel() // C
     y = torch.empty_like(z)
-    check(lib().fs2k_affine_act(_p(z), _p(scale), _p(shift), _ACTS[act], _p(residual), M, C, _p(y), _stream()), "fs2k_affine_act")
+    check(lib().fs2k_affine_act(_p(z), _p(scale), _p(shift), _ACTS[act], _p(residual), M, C, float(dropout_p), int(seed), _p(y), _stream()), "fs2k_affine_act")
     _count()
     return y
 
@@ -258,15 +259,20 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
     N, K, taps = weight.shape
     if taps == 1:
         return weight.detach().reshape(1, N, K)
+    # keyed on the tensor OBJECT (weak reference): id()/data_ptr()/_version alone can all be reused by a new
+    # parameter allocated at a freed one's address, which would hand back another model's weights
     key = (weight.data_ptr(), weight._version, tuple(weight.shape))
     hit = _repack_cache.get(id(weight))
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and hit[2]() is weight:
         return hit[1]
     w = _f32(weight.detach(), "weight")
     out = torch.empty((taps, N, K), dtype=torch.float32, device=w.device)
     check(lib().fs2k_repack_conv_weight(_p(w), N, K, taps, _p(out), _stream()), "fs2k_repack_conv_weight")
     _count()
-    _repack_cache[id(weight)] = (key, out)
+    if len(_repack_cache) > 512:  # drop entries whose parameter is gone
+        for k in [k for k, v in _repack_cache.items() if v[2]() is None]:
+            del _repack_cache[k]
+    _repack_cache[id(weight)] = (key, out, weakref.ref(weight))
     return out
 
 
@@ -510,10 +516,10 @@ def gather_rows(table, ids):
     return out
 
 
-def dropout(x, p: float, seed: int):
+def dropout(x, p: float, seed: int, residual=None):
     x = _f32(x, "x")
     y = torch.empty_like(x)
-    check(lib().fs2k_dropout(_p(x), float(p), int(seed), x.numel(), _p(y), _stream()), "fs2k_dropout")
+    check(lib().fs2k_dropout(_p(x), _p(residual), float(p), int(seed), x.numel(), _p(y), _stream()), "fs2k_dropout")
     _count()
     return y
 
@@ -532,14 +538,14 @@ def tanh(x):
 _ACT_BWD_MODE = {None: 0, "none": 0, "relu": 1, "silu": 2, "tanh": 3}
 
 
-def act_bwd(g, aux, act, alpha: float = 1.0, row_mask=None):
+def act_bwd(g, aux, act, alpha: float = 1.0, row_mask=None, dropout_p: float = 0.0, seed: int = 0):
     g = _f32(g, "g")
     C = g.shape[-1]
     M = g.numel() // C
     gz = torch.empty_like(g)
     if row_mask is not None:
         row_mask = row_mask.contiguous()
-    check(lib().fs2k_act_bwd(_p(g), _p(aux), _ACT_BWD_MODE[act], float(alpha), _p(row_mask), M, C, _p(gz), _stream()), "fs2k_act_bwd")
+    check(lib().fs2k_act_bwd(_p(g), _p(aux), _ACT_BWD_MODE[act], float(alpha), _p(row_mask), M, C, float(dropout_p), int(seed), _p(gz), _stream()), "fs2k_act_bwd")
     _count()
     return gz
 
@@ -593,19 +599,19 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool):
     return out
 
 
-def layernorm_bwd(g, x, mean, rstd, gamma):
+def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0):
     g, x = _f32(g, "g"), _f32(x, "x")
     D = x.shape[-1]
     M = x.numel() // D
     dx = torch.empty_like(x)
     dgamma = torch.empty((D,), dtype=torch.float32, device=x.device)
     dbeta = torch.empty((D,), dtype=torch.float32, device=x.device)
-    check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, _p(dx), _p(dgamma), _p(dbeta), _stream()), "fs2k_layernorm_bwd")
+    check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, float(dropout_p), int(seed), _p(dx), _p(dgamma), _p(dbeta), _stream()), "fs2k_layernorm_bwd")
     _count()
     return dx, dgamma, dbeta
 
 
-def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool):
+def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: float = 0.0, seed: int = 0):
     g, z = _f32(g, "g"), _f32(z, "z")
     C = z.shape[-1]
     M = z.numel() // C
@@ -614,7 +620,7 @@ def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool):
     dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
     dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
     check(lib().fs2k_bn_act_bwd(_p(g), _p(z), _p(scale), _p(shift), _p(mean), _p(rstd), _ACTS[act], int(training), M, C,
-                                _p(sums), _p(gz), _p(dgamma), _p(dbeta), _stream()), "fs2k_bn_act_bwd")
+                                float(dropout_p), int(seed), _p(sums), _p(gz), _p(dgamma), _p(dbeta), _stream()), "fs2k_bn_act_bwd")
     _count(2)
     return gz, dgamma, dbeta
 

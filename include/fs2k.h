@@ -98,8 +98,8 @@ int fs2k_mask_lens(const uint8_t* mask, int B, int L, int* lens, fs2k_stream_t s
 /* ---- normalisation ------------------------------------------------------------------------------
  * LayerNorm over the last dim (eps 1e-5): torchaudio conformer.py:41,103,151,165; fs2/layers.py:42.
  * mean_out / rstd_out (optional, [M]) are saved for the backward pass. */
-int fs2k_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, long M, int D, float* y,
-                       float* mean_out, float* rstd_out, fs2k_stream_t stream);
+int fs2k_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, long M, int D, float dropout_p,
+                       long seed, float* y, float* mean_out, float* rstd_out, fs2k_stream_t stream);
 /* BatchNorm1d (conformer.py:62-64, fs2/layers.py:168-202): colstats = per-channel sum / sum-of-squares of
  * z[M,C] in fp64 (sums[2C], zeroed here); bn_finalize turns them (training) or the running stats (eval)
  * into scale/shift and, in training, updates running_mean/var (momentum, unbiased var) in place. */
@@ -108,9 +108,9 @@ int fs2k_bn_finalize(const double* sums, long M, int C, const float* gamma, cons
                      float momentum, int training, float* running_mean, float* running_var,
                      long long* num_batches_tracked, float* scale, float* shift, float* save_mean, float* save_rstd,
                      fs2k_stream_t stream);
-/* y = act(z*scale[c] + shift[c]) (+ residual) */
+/* y = dropout(act(z*scale[c] + shift[c])) (+ residual); scale == NULL: plain activation; dropout_p == 0: none */
 int fs2k_affine_act(const float* z, const float* scale, const float* shift, int act, const float* residual, long M,
-                    int C, float* y, fs2k_stream_t stream);
+                    int C, float dropout_p, long seed, float* y, fs2k_stream_t stream);
 
 /* ---- dense contractions ---------------------------------------------------------------------------
  * C[(b,l),n] = (act((sum_tap sum_k A[b,l+tap-pad,k] W[tap][n][k] + bias[n]) * scale[n] + shift[n]) * alpha
@@ -177,7 +177,7 @@ int fs2k_bin_loss_bwd(const float* hard, const float* soft, long N, float eps, c
  *           forward fs2k_gemm_* call on gz).  unpack_conv_weight: [taps][N][K] → PyTorch [N][K][taps].
  * gemm_wgrad: dW[tap][n][k] = Σ_(b,l) G[b,l,n] · X[b,l+tap-pad,k]  (dW zeroed here, split over rows + atomics). */
 int fs2k_act_bwd(const float* g, const float* aux, int mode, float alpha, const uint8_t* row_mask, long M, int C,
-                 float* gz, fs2k_stream_t stream);
+                 float dropout_p, long seed, float* gz, fs2k_stream_t stream);
 int fs2k_colsum(const float* z, long M, int C, float* out, fs2k_stream_t stream);
 int fs2k_repack_weight_t(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
 int fs2k_unpack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
@@ -193,13 +193,14 @@ int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int ldx, int B, 
                        int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout, fs2k_stream_t stream);
 /* LayerNorm backward (dgamma/dbeta zeroed here, accumulated with atomics) */
 int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       long M, int D, float* dx, float* dgamma, float* dbeta, fs2k_stream_t stream);
+                       long M, int D, float dropout_p, long seed, float* dx, float* dgamma, float* dbeta,
+                       fs2k_stream_t stream);
 /* BatchNorm1d (+ activation) backward: y = act(z*scale + shift), zhat = (z - mean)*rstd.
  * training: gz = scale*(gu - mean(gu) - zhat*mean(gu*zhat)); eval: gz = gu*scale; dgamma = Σ gu*zhat, dbeta = Σ gu.
  * sums: 2C doubles of scratch. */
 int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift, const float* mean,
-                    const float* rstd, int act, int training, long M, int C, double* sums, float* gz, float* dgamma,
-                    float* dbeta, fs2k_stream_t stream);
+                    const float* rstd, int act, int training, long M, int C, float dropout_p, long seed, double* sums,
+                    float* gz, float* dgamma, float* dbeta, fs2k_stream_t stream);
 /* attention backward (flash style, recomputes P from lse); delta: [B,H,L] scratch; dqkv [B,L,3·H·hd] */
 int fs2k_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, const int* lens,
                            int B, int L, int H, int head_dim, float dropout_p, long seed, float* delta, float* dqkv,
@@ -235,8 +236,10 @@ int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float 
 int fs2k_axpby(const float* a, float alpha, const float* b, float beta, long N, float* out, fs2k_stream_t stream);
 int fs2k_gather_rows(const float* table, const long long* ids, long R, int D, float* out, fs2k_stream_t stream);
 int fs2k_tanh(const float* x, long N, float* y, fs2k_stream_t stream);
-/* dropout: y = x·keep/(1-p), keep from a counter hash of (seed, index); the backward calls it again on the gradient */
-int fs2k_dropout(const float* x, float p, long seed, long N, float* y, fs2k_stream_t stream);
+/* dropout: y = x·keep/(1-p) (+ residual), keep from a counter hash of (seed, index); the backward calls it again on
+ * the gradient.  The same mask can be fused into fs2k_affine_act / fs2k_layernorm_fwd (forward) and
+ * fs2k_act_bwd / fs2k_bn_act_bwd / fs2k_layernorm_bwd (backward) through their (dropout_p, seed) arguments. */
+int fs2k_dropout(const float* x, const float* residual, float p, long seed, long N, float* y, fs2k_stream_t stream);
 
 #ifdef __cplusplus
 }
