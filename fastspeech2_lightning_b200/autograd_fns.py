@@ -507,5 +507,23 @@ def attn_bin_loss(hard, soft, eps=1e-12):
     return _BinLoss.apply(hard.detach().contiguous(), soft.contiguous(), float(eps))
 
 
+class _CtcForwardSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attn_logprob, key_lens, query_lens, blank_logprob):
+        loss, saved = ops.ctc_forward_sum_fwd(attn_logprob, key_lens, query_lens, blank_logprob)
+        ctx.save_for_backward(*saved)
+        ctx.blank = blank_logprob
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return ops.ctc_forward_sum_bwd(ctx.saved_tensors, g.contiguous(), ctx.blank), None, None, None
+
+
+def ctc_forward_sum(attn_logprob, key_lens, query_lens, blank_logprob=-1.0):
+    return _CtcForwardSum.apply(attn_logprob.contiguous(), key_lens, query_lens, float(blank_logprob))
+
+
 def tanh_row(table, index):
     return ops.tanh(table.detach()[index: index + 1].contiguous())

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                    const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
                    float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+    seed = seed_with_base(seed);
     constexpr int BQ = 64, BKEY = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;               // [BQ][QS]
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                     const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
                     float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+    seed = seed_with_base(seed);
     constexpr int BKEY = 64, BQ = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Ks = smem;               // [BKEY][QS]
@@ -323,3 +325,5 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(attention_bwd)

@@ -19,6 +19,7 @@ template <int HD>
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ lens, int L, int H, float scale,
                       float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ lse_out) {
+    seed = seed_with_base(seed);
     constexpr int QS = HD + 4, PS = ABK + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;                 // [ABQ][QS]
@@ -186,3 +187,5 @@ extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int 
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(attention)

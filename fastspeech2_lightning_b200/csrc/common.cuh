@@ -64,6 +64,21 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
     z ^= z >> 31;
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
+// Dropout under CUDA-graph replay: the by-value seeds of a captured launch are frozen, so every dropout kernel
+// adds *g_seed_base (a device counter the host rewrites before each replay; null → 0) to its seed on entry.
+// One copy of the pointer per translation unit; FS2K_DEFINE_SEED_BASE_SETTER(tag) exports its setter and
+// fs2k_set_dropout_seed_base (lib.cu) fans out to all of them.
+static __device__ const unsigned long long* g_seed_base = nullptr;
+__device__ __forceinline__ unsigned long long seed_with_base(unsigned long long seed) {
+    const unsigned long long* p = g_seed_base;
+    return p ? seed + *p : seed;
+}
+#define FS2K_DEFINE_SEED_BASE_SETTER(tag)                                                                  \
+    extern "C" int fs2k_seed_base_set_##tag(const void* dev_ptr) {                                        \
+        cudaError_t e = cudaMemcpyToSymbol(fs2k::g_seed_base, &dev_ptr, sizeof(dev_ptr));                  \
+        return e == cudaSuccess ? FS2K_OK : fs2k_set_cuda_error(e);                                        \
+    }
+
 // scaled keep mask of attention-probability dropout for element (b,h,q,k)
 __device__ __forceinline__ float attn_keep(unsigned long long seed, float p, float inv_keep, int b, int h, int q, int k,
                                            int H, int L) {

@@ -8,6 +8,7 @@ namespace fs2k {
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, const float* __restrict__ residual, float p, float inv_keep,
                unsigned long long seed, long N, float* __restrict__ y) {
+    seed = seed_with_base(seed);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const float v = hash_uniform(seed, (unsigned long long)i) >= p ? x[i] * inv_keep : 0.f;
         y[i] = residual ? v + residual[i] : v;
@@ -27,3 +28,5 @@ extern "C" int fs2k_dropout(const float* x, const float* residual, float p, long
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(dropout)

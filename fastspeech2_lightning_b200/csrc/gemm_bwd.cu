@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int mode, float alpha,
                const uint8_t* __restrict__ row_mask, long M, int C, float drop_p, unsigned long long seed,
                float* __restrict__ gz) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
@@ -232,3 +233,5 @@ extern "C" int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx,
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(gemm_bwd)

@@ -49,3 +49,21 @@ extern "C" int fs2k_spin_ns(long ns, fs2k_stream_t stream) {
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+// every translation unit with dropout kernels keeps its own copy of the seed-base pointer (common.cuh)
+extern "C" int fs2k_seed_base_set_attention_bwd(const void*);
+extern "C" int fs2k_seed_base_set_attention(const void*);
+extern "C" int fs2k_seed_base_set_dropout(const void*);
+extern "C" int fs2k_seed_base_set_gemm_bwd(const void*);
+extern "C" int fs2k_seed_base_set_norms(const void*);
+extern "C" int fs2k_seed_base_set_norms_bwd(const void*);
+
+extern "C" int fs2k_set_dropout_seed_base(const unsigned long long* device_counter) {
+    int (*setters[])(const void*) = {fs2k_seed_base_set_attention_bwd, fs2k_seed_base_set_attention, fs2k_seed_base_set_dropout,
+                                     fs2k_seed_base_set_gemm_bwd,      fs2k_seed_base_set_norms,     fs2k_seed_base_set_norms_bwd};
+    for (auto f : setters) {
+        const int r = f(device_counter);
+        if (r != FS2K_OK) return r;
+    }
+    return FS2K_OK;
+}

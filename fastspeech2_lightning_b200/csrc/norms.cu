@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, long M, int D, float drop_p, unsigned long long seed, float* __restrict__ y,
                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int lane = threadIdx.x & 31;
     const int D4 = D >> 2;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   int act, const float* __restrict__ residual, long M, int C, float drop_p, unsigned long long seed,
                   float* __restrict__ y) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
@@ -242,3 +244,5 @@ extern "C" int fs2k_affine_act(const float* z, const float* scale, const float* 
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(norms)

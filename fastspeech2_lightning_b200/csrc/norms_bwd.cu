@@ -10,6 +10,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                      const float* __restrict__ rstd, const float* __restrict__ gamma, long M, int D, float drop_p,
                      unsigned long long seed, float* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ float s_red[8][32 * MAXV * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -101,6 +102,7 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                     int act, long M, int C, long rows_per_cta, float drop_p, unsigned long long seed,
                     double* __restrict__ sums) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ double s_part[8][128][2];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -156,6 +158,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     const double* __restrict__ sums, int act, int training, long M, int C, float drop_p,
                     unsigned long long seed, float* __restrict__ gz, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
+    seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
     const long N = M * C4;
@@ -238,3 +241,5 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(norms_bwd)

@@ -30,7 +30,12 @@ sumsq_kernel(const float* __restrict__ g, long N, double* __restrict__ out) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long N,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
-             float grad_scale, const double* __restrict__ sumsq) {
+             float grad_scale, const double* __restrict__ sumsq, const float* __restrict__ step_state) {
+    if (step_state) {  // graph replay: the step's scalars come from device memory
+        lr = step_state[0];
+        bc1 = step_state[1];
+        bc2_sqrt = step_state[2];
+    }
     float clip = grad_scale;
     if (sumsq) {
         const float total = (float)sqrt(sumsq[0]) * grad_scale;
@@ -79,7 +84,38 @@ extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, lon
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     adamw_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                             bc2_sqrt, max_norm, grad_scale, sumsq);
+                                                             bc2_sqrt, max_norm, grad_scale, sumsq, nullptr);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+extern "C" int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v, long N, const float* step_state,
+                                   float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                                   float grad_scale, const double* sumsq, fs2k_stream_t stream) {
+    FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
+    if (N == 0) return FS2K_OK;
+    FS2K_REQUIRE(p && g && m && v && step_state, FS2K_ERR_NULL);
+    long grid = (N + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    adamw_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, N, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
+                                                             max_norm, grad_scale, sumsq, step_state);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+namespace fs2k {
+__global__ void set_step_state_kernel(float* __restrict__ st, unsigned long long* __restrict__ seed_base, float lr, float bc1,
+                                      float bc2_sqrt, unsigned long long base) {
+    if (st) { st[0] = lr; st[1] = bc1; st[2] = bc2_sqrt; st[3] = 0.f; }
+    if (seed_base) seed_base[0] = base;
+}
+}  // namespace fs2k
+
+extern "C" int fs2k_set_step_state(float* step_state, unsigned long long* seed_base, float lr, float bias_correction1,
+                                   float bias_correction2_sqrt, long seed_base_value, fs2k_stream_t stream) {
+    FS2K_REQUIRE(step_state || seed_base, FS2K_ERR_NULL);
+    set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_state, seed_base, lr, bias_correction1, bias_correction2_sqrt,
+                                                            (unsigned long long)seed_base_value);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -270,6 +270,23 @@ class FastSpeech2(_Base):
             self.variance_adaptor.validate_durations = False
         return self
 
+    def optimization_step(self, batch, use_cuda_graph: bool = True):
+        """training_step + backward + clip + optimizer.step + scheduler.step — what Lightning's fit loop does around
+        `training_step` (fs2/model.py:384-390, fs2/cli/train.py:38) — as one call.  With `use_cuda_graph` the whole
+        step of a repeated batch shape is one CUDA-graph replay (graphs.GraphedTrainStep).  Needs
+        `configure_optimizers()` first.  Returns the dict of loss tensors (device scalars, no host read)."""
+        runner = getattr(self, "_train_runner", None)
+        if runner is None or runner.opt is not self.optimizer:
+            from ..graphs import GraphedTrainStep
+
+            runner = self._train_runner = GraphedTrainStep(self, self.optimizer, self.scheduler)
+        if use_cuda_graph:
+            return runner(batch)
+        dev = self.optimizer.flat_p.device
+        losses = runner._step_body({k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()})
+        self.scheduler.step()
+        return losses
+
     def predict_step(self, batch, batch_idx):
         graphed = getattr(self, "_graphed", None)
         if graphed is not None and batch.get("mel_lens") is not None and not self.training:

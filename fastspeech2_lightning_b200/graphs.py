@@ -1,4 +1,4 @@
-"""CUDA-graph replay of the synthesis forward.
+"""CUDA-graph replay of the synthesis forward and of the whole training step.
 
 The model is small (≈200 kernel launches, ≈0.2 TFLOP per batch), so an eager step is bound by host
 launch latency, not by the GPU.  `GraphedSynthesis` captures `model(batch, inference=True)` once per
@@ -9,6 +9,8 @@ i.e. given durations (teacher-forced synthesis) with `validate_durations = False
 from __future__ import annotations
 
 import torch
+
+from ._lib import lib
 
 
 def _signature(batch) -> tuple:
@@ -61,3 +63,86 @@ class GraphedSynthesis:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         graph.replay()
         return static_out
+
+
+
+class GraphedTrainStep:
+    """One optimisation step — zero_grad, forward (aligner + MAS + encoder + variance adaptor + decoder + PostNet),
+    the seven losses, backward, (NCCL all-reduce of the flat gradient), clip and AdamW — as ONE CUDA graph per batch
+    shape: ≈1000 kernel launches become one `cudaGraphLaunch`, so a step costs what the GPU needs, not what Python
+    can enqueue.
+
+    Everything that changes between steps lives in device memory: the batch (copied into the captured input
+    buffers, straight from pinned host memory if that is where it is), the learning rate / Adam bias corrections
+    and the dropout seed base (`FusedAdamW.begin_graph_step`).  The first time a shape is seen the step runs
+    eagerly (that is also the warm-up a capture needs); the second time it is captured and replayed.  Shapes are
+    exact — padding is live in this model (BatchNorm statistics and the full-rectangle losses see it), so batches
+    are never re-padded to share a graph.  The loss weights that depend on the epoch are part of the key.
+    """
+
+    def __init__(self, model, optimizer, scheduler=None, max_graphs: int = 16):
+        self.model, self.opt, self.sched = model, optimizer, scheduler
+        self.max_graphs = max_graphs
+        self._cache: dict = {}
+        self._seen: set = set()
+        self._pool = None
+        lib().fs2k_set_dropout_seed_base(optimizer.seed_base.data_ptr())
+
+    def _step_body(self, batch):
+        model, opt = self.model, self.opt
+        opt.zero_grad()
+        out = model(batch)
+        losses = model.loss(out, batch, model.current_epoch)
+        losses["total"].backward()
+        opt.step()
+        # detached: a loss that kept its autograd graph alive would also keep this step's AccumulateGrad nodes (and
+        # their stream) alive into the next capture
+        return {k: v.detach() for k, v in losses.items()}
+
+    def _key(self, batch):
+        t = self.model.config.training
+        return _signature(batch), min(self.model.current_epoch, t.attn_bin_loss_warmup_epochs)
+
+    def __call__(self, batch, non_blocking: bool = True):
+        """batch: collated dict (CUDA or pinned-host tensors).  Returns the dict of loss tensors (device scalars;
+        static buffers of the graph — read or copy them before the next call)."""
+        model, opt = self.model, self.opt
+        key = self._key(batch)
+        entry = self._cache.get(key)
+        dev = opt.flat_p.device
+        if entry is None and key not in self._seen:
+            # first sight of this shape: plain eager step (validates the data, warms every lazy init)
+            self._seen.add(key)
+            dev_batch = {k: (v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+            losses = self._step_body(dev_batch)
+            if self.sched is not None:
+                self.sched.step()
+            return losses
+        if entry is None:
+            if len(self._cache) >= self.max_graphs:
+                self._cache.pop(next(iter(self._cache)))
+            static_in = {k: (v.to(dev).clone() if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+            va = model.variance_adaptor
+            prev_validate, va.validate_durations = va.validate_durations, False  # the eager first sight validated
+            opt.device_state = True
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph, pool=self._pool):
+                    static_losses = self._step_body(static_in)
+            finally:
+                opt.device_state = False
+                va.validate_durations = prev_validate
+            if self._pool is None:
+                self._pool = graph.pool()
+            entry = (graph, static_in, static_losses)
+            self._cache[key] = entry
+        graph, static_in, static_losses = entry
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.dim() > 0:
+                static_in[k].copy_(v, non_blocking=non_blocking)
+        opt.begin_graph_step()
+        graph.replay()
+        if self.sched is not None:
+            self.sched.step()
+        return static_losses

@@ -495,6 +495,32 @@ def bin_loss_bwd(hard, soft, eps: float, sums, gout):
     return dsoft
 
 
+def ctc_forward_sum_fwd(attn_logprob, key_lens, query_lens, blank_logprob: float = -1.0):
+    """Forward-sum loss of attn_logprob [B,1,F,T] (attention_loss.py:22-62) → (loss 0-d, saved tensors for the backward)."""
+    x = _f32(attn_logprob, "attn_logprob")
+    B, F, T = x.shape[0], x.shape[-2], x.shape[-1]
+    kl, ql = _i32(key_lens, "key_lens"), _i32(query_lens, "query_lens")
+    dev = x.device
+    lse = torch.empty((B, F), dtype=torch.float64, device=dev)
+    log_alpha = torch.empty((B, F, 2 * T + 1), dtype=torch.float64, device=dev)
+    nll = torch.empty((B,), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    check(lib().fs2k_ctc_forward_sum_fwd(_p(x), _p(kl), _p(ql), B, F, T, float(blank_logprob), _p(lse), _p(log_alpha), _p(nll), _p(loss), _stream()),
+          "fs2k_ctc_forward_sum_fwd")
+    _count(2)
+    return loss, (x, lse, log_alpha, nll, kl, ql)
+
+
+def ctc_forward_sum_bwd(saved, gout, blank_logprob: float = -1.0):
+    x, lse, log_alpha, nll, kl, ql = saved
+    B, F, T = x.shape[0], x.shape[-2], x.shape[-1]
+    dx = torch.empty_like(x)
+    check(lib().fs2k_ctc_forward_sum_bwd(_p(x), _p(lse), _p(log_alpha), _p(nll), _p(kl), _p(ql), _p(_f32(gout)), B, F, T, float(blank_logprob), _p(dx), _stream()),
+          "fs2k_ctc_forward_sum_bwd")
+    _count()
+    return dx
+
+
 def axpby(a, alpha: float, b=None, beta: float = 0.0):
     a = _f32(a, "a")
     if b is not None:

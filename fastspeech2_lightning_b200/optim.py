@@ -46,6 +46,11 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = self.flat_g[o: o + p.numel()].view_as(p)
         self._params, self._offs, self.numel = params, offs, n
         self._step = 0
+        # device copies of the per-step scalars {lr, 1−β1^t, sqrt(1−β2^t)} and the dropout seed base: a captured
+        # (CUDA-graph) step reads them instead of by-value arguments — see begin_graph_step()
+        self.step_state = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.seed_base = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.device_state = False  # True while a step is being captured: step() must not touch host scalars
 
     def zero_grad(self, set_to_none: bool = False):
         """Gradients stay views of the flat buffer (never set to None): one memset."""
@@ -69,9 +74,20 @@ class FusedAdamW(torch.optim.Optimizer):
             if world > 1:  # data-parallel exchange: one all-reduce of the flat gradient; the mean folds into the update
                 torch.distributed.all_reduce(self.flat_g, group=self.process_group)
         g = self.param_groups[0]
-        self._step += 1
         stream = torch.cuda.current_stream().cuda_stream
         sumsq = None
+        if self.device_state:
+            if self.max_grad_norm is not None:
+                check(lib().fs2k_sumsq(self.flat_g.data_ptr(), self.flat_g.numel(), self._sumsq.data_ptr(), stream), "fs2k_sumsq")
+                ops._count()
+                sumsq = self._sumsq.data_ptr()
+            check(lib().fs2k_adamw_step_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                            self.flat_p.numel(), self.step_state.data_ptr(), float(g["betas"][0]), float(g["betas"][1]),
+                                            float(g["eps"]), float(g["weight_decay"]), float(self.max_grad_norm or 0.0), 1.0 / world,
+                                            sumsq, stream), "fs2k_adamw_step_dev")
+            ops._count()
+            return loss
+        self._step += 1
         if self.max_grad_norm is not None:
             check(lib().fs2k_sumsq(self.flat_g.data_ptr(), self.flat_g.numel(), self._sumsq.data_ptr(), stream), "fs2k_sumsq")
             ops._count()
@@ -82,3 +98,17 @@ class FusedAdamW(torch.optim.Optimizer):
               "fs2k_adamw_step")
         ops._count()
         return loss
+
+
+    def begin_graph_step(self) -> None:
+        """Host side of one replayed step: advance the step count and publish this step's learning rate, bias
+        corrections and a fresh dropout seed base to the device (one tiny launch, arguments by value)."""
+        g = self.param_groups[0]
+        self._step += 1
+        self._opt_called = True  # LRScheduler's "scheduler.step() before optimizer.step()" check
+        b1, b2 = g["betas"]
+        seed = int(torch.randint(0, 2**62, (1,)).item())
+        check(lib().fs2k_set_step_state(self.step_state.data_ptr(), self.seed_base.data_ptr(), float(g["lr"]), 1.0 - b1 ** self._step,
+                                        (1.0 - b2 ** self._step) ** 0.5, seed, torch.cuda.current_stream().cuda_stream),
+              "fs2k_set_step_state")
+        ops._count()

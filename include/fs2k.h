@@ -168,6 +168,19 @@ int fs2k_bin_loss_fwd(const float* hard, const float* soft, long N, float eps, d
                       fs2k_stream_t stream);
 int fs2k_bin_loss_bwd(const float* hard, const float* soft, long N, float eps, const double* sums, const float* gout,
                       float* dsoft, fs2k_stream_t stream);
+/* AttentionCTCLoss / ForwardSumLoss (fs2/attn/attention_loss.py:22-62), fused: blank column (log-prob
+ * blank_logprob) + key mask + log_softmax over the key_len+1 classes + CTC α recursion with targets 1..key_len,
+ * input length query_len, reduction "mean" (nll/key_len averaged over B), zero_infinity.
+ * attn_logprob [B,F,T] (the [B,1,F,T] aligner output); lse [B,F], log_alpha [B,F,2T+1] (fs2k_ctc_alpha_elems
+ * elements) and nll [B] are fp64 (the recursion runs in fp64) and are kept for the backward; loss: one float.  The backward writes the gradient with
+ * respect to attn_logprob itself (through the log_softmax and the padding), scaled by the device scalar gout. */
+size_t fs2k_ctc_alpha_elems(int B, int F, int T);
+int fs2k_ctc_forward_sum_fwd(const float* attn_logprob, const int* key_lens, const int* query_lens, int B, int F,
+                             int T, float blank_logprob, double* lse, double* log_alpha, double* nll, float* loss,
+                             fs2k_stream_t stream);
+int fs2k_ctc_forward_sum_bwd(const float* attn_logprob, const double* lse, const double* log_alpha, const double* nll,
+                             const int* key_lens, const int* query_lens, const float* gout, int B, int F, int T,
+                             float blank_logprob, float* d_attn_logprob, fs2k_stream_t stream);
 
 /* ---- backward kernels (training step: fs2/model.py:384-390 + Lightning's backward) ----------------------
  * Every forward entry point above has its gradient here; torch.autograd only sequences the calls.
@@ -231,6 +244,16 @@ int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t stream);
 int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float lr, float beta1, float beta2, float eps,
                     float weight_decay, long step, float max_norm, float grad_scale, const double* sumsq,
                     fs2k_stream_t stream);
+/* CUDA-graph replay of a whole training step: per-step scalars live in device memory so that a captured launch
+ * sees fresh values.  step_state = 4 floats {lr, 1−β1^t, sqrt(1−β2^t), unused}; set_step_state writes them and the
+ * dropout seed base in one tiny launch (by-value kernel arguments, so no host staging buffer can race).
+ * set_dropout_seed_base registers the device counter every dropout kernel adds to its seed (NULL = none). */
+int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v, long N, const float* step_state, float beta1,
+                        float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                        const double* sumsq, fs2k_stream_t stream);
+int fs2k_set_step_state(float* step_state, unsigned long long* seed_base, float lr, float bias_correction1,
+                        float bias_correction2_sqrt, long seed_base_value, fs2k_stream_t stream);
+int fs2k_set_dropout_seed_base(const unsigned long long* device_counter);
 
 /* ---- small elementwise helpers ------------------------------------------------------------------------ */
 int fs2k_axpby(const float* a, float alpha, const float* b, float beta, long N, float* out, fs2k_stream_t stream);

@@ -254,3 +254,43 @@ def test_training_step_gradients_match_reference(name, bwd, request):
         if k.startswith("bn."):
             close(model.state_dict()[k[3:]], want, 1e-4, k)
     print(f"{name}: worst relative gradient-norm error {worst:.2e} over {len(gold['grad.norms'])} parameters")
+
+
+@pytest.mark.parametrize("B,F,T,case", [(4, 60, 12, "ragged"), (3, 33, 40, "impossible"), (32, 500, 80, "c2"), (2, 700, 300, "long")])
+def test_ctc_forward_sum_kernel_matches_torch_ctc(B, F, T, case):
+    """csrc/ctc.cu against the reference composition (pad blank, mask keys, log_softmax, nn.CTCLoss) evaluated
+    by the oracle on the CPU: loss and gradient w.r.t. attn_logprob.  'impossible': query_len < key_len for one
+    utterance → infinite nll → zero_infinity zeroes that utterance's loss and gradient."""
+    from fastspeech2_lightning_b200 import autograd_fns as fns
+    from oracle.fs2_oracle import attention_ctc_loss
+
+    g = torch.Generator().manual_seed(B * 1000 + F)
+    # the oracle composition evaluated in fp64 is the truth; torch's own fp32 recursion carries ≈1e-3 of rounding
+    # noise on the posteriors at F = 500 (|α| ≈ 1500, fp32 spacing 1e-4), the kernel recurses in fp64
+    x = (torch.randn(B, 1, F, T, generator=g) * 2.0).double().requires_grad_(True)
+    key_lens = torch.randint(max(T // 2, 1), T + 1, (B,), generator=g)
+    query_lens = torch.randint(max(F // 2, T), F + 1, (B,), generator=g) if case != "impossible" else torch.tensor([F, 10, F])
+    key_lens[0], query_lens[0] = T, F
+    if case == "impossible":
+        key_lens[1] = 30  # 10 frames cannot emit 30 tokens
+    ref = attention_ctc_loss(x, key_lens, query_lens)
+    (ref * 1.7).backward()
+    xd = x.detach().float().to(DEV).requires_grad_(True)
+    out = fns.ctc_forward_sum(xd, key_lens.to(DEV), query_lens.to(DEV), -1.0)
+    (out * 1.7).backward()
+    assert abs(float(out.detach()) - float(ref.detach())) <= 2e-6 * max(1.0, abs(float(ref.detach()))), (float(out.detach()), float(ref.detach()))
+    gref, ggpu = x.grad, xd.grad.cpu().double()
+    err = float((gref - ggpu).abs().max()) / max(float(gref.abs().max()), 1e-30)
+    assert err <= 2e-6, err
+    if case == "c2":  # and the reference's own fp32 arithmetic agrees within its noise
+        x32 = x.detach().float().requires_grad_(True)
+        r32 = attention_ctc_loss(x32, key_lens, query_lens)
+        (r32 * 1.7).backward()
+        assert abs(float(r32.detach()) - float(out.detach())) <= 1e-4 * abs(float(r32.detach()))
+        assert float((x32.grad.double() - ggpu).abs().max()) / float(gref.abs().max()) <= 1e-2
+    # gradient past the utterance and for masked keys is exactly zero
+    for b in range(B):
+        assert float(ggpu[b, 0, int(query_lens[b]):].abs().max() if int(query_lens[b]) < F else 0.0) == 0.0
+        assert float(ggpu[b, 0, :, int(key_lens[b]):].abs().max() if int(key_lens[b]) < T else 0.0) == 0.0
+    if case == "impossible":
+        assert float(ggpu[1].abs().max()) == 0.0

@@ -90,3 +90,62 @@ def test_training_run_reduces_the_loss():
     assert all(torch.isfinite(p).all() for p in model.parameters())
     assert last < first, (first, last)
     assert "training/total_loss" in model.logged
+
+
+def _fresh_model(meta, clip=1.0):
+    model = build_model(meta)
+    model.fused_grad_clip = clip
+    model.configure_optimizers()
+    return model
+
+
+def test_graph_replayed_training_step_matches_eager_steps():
+    """graphs.GraphedTrainStep: first sight eager, then capture + replay.  Same batches, dropout off → the loss
+    trajectory and the parameters follow the eager run (differences only from the fp64 atomics' summation order)."""
+    meta, _ = load_case("train_bn")
+    batch = case_batch(meta, DEV)
+    runs = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        model = _fresh_model(meta)
+        traj = []
+        for i in range(5):
+            losses = model.optimization_step(batch, use_cuda_graph=(mode == "graph"))
+            traj.append({k: float(v) for k, v in losses.items()})
+        runs[mode] = (traj, [p.detach().clone() for p in model.parameters()], model)
+    assert len(runs["graph"][2]._train_runner._cache) == 1  # captured once, replayed three times
+    for a, b in zip(runs["eager"][0], runs["graph"][0]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    assert runs["eager"][0][-1]["total"] < runs["eager"][0][0]["total"]
+    worst = max(float((p - q).abs().max()) for p, q in zip(runs["eager"][1], runs["graph"][1]))
+    assert worst < 5e-4, worst
+    assert runs["graph"][2].optimizer._step == 5 and runs["graph"][2].scheduler.last_epoch == 5
+
+
+def test_graph_replay_draws_fresh_dropout_masks_and_learning_rates():
+    """By-value seeds are frozen inside a captured launch; the per-step seed base in device memory must still give
+    every replay its own masks, and the learning rate must come from device memory (Noam moves it every step)."""
+    meta, _ = load_case("train_bn")
+    batch = case_batch(meta, DEV)
+    model = _fresh_model(meta)
+    model.postnet.dropout_in_training = True
+    for g in model.optimizer.param_groups:
+        g["weight_decay"] = 0.0
+    model.scheduler.base_lrs = [0.0 for _ in model.scheduler.base_lrs]  # frozen parameters: only dropout varies
+    seen = []
+    for i in range(4):
+        losses = model.optimization_step(batch)
+        seen.append({k: float(v) for k, v in losses.items()})
+    replays = seen[1:]
+    assert len({round(r["postnet"], 9) for r in replays}) == len(replays), replays  # fresh PostNet dropout masks
+    assert all(abs(r["spec"] - replays[0]["spec"]) < 1e-6 for r in replays)          # no dropout before the PostNet
+    # now let the schedule drive the captured optimizer: parameters must move by the current lr, not the captured one
+    model.scheduler.base_lrs = [1e-3 for _ in model.scheduler.base_lrs]
+    before = model.optimizer.flat_p.clone()
+    model.scheduler.step()
+    lr_now = model.optimizer.param_groups[0]["lr"]
+    assert lr_now > 0
+    model.optimization_step(batch)
+    moved = float((model.optimizer.flat_p - before).abs().max())
+    assert 0 < moved <= 1.01 * lr_now * 1.5, (moved, lr_now)  # |Δp| ≤ lr·|m̂/√v̂| — bounded by ≈ lr early in training
