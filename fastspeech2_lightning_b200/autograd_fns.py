@@ -71,10 +71,49 @@ def layernorm(x, weight, bias, eps, dropout_p=0.0):
 
 
 # ---------------------------------------------------------------------------------------------
-def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b):
+class WgradSink:
+    """Weight/bias gradients off the critical path.  The data-gradient chain (dgrad GEMM → LayerNorm backward → …) is
+    what the next backward node waits for; a weight gradient is a leaf.  With a sink installed every contraction's
+    wgrad + bias column-sum runs on a second stream and accumulates straight into `param.grad` (FusedAdamW's flat
+    gradient buffer), autograd receives None for those inputs (no AccumulateGrad launch), and `join()` — called once
+    before the optimizer — makes the main stream wait for the side stream.  Under CUDA-graph capture the two streams
+    become parallel branches of the graph.  Gradient tensors read by the side stream are kept referenced until the
+    join so the allocator cannot hand their memory to a later main-stream kernel."""
+
+    def __init__(self):
+        self.stream = torch.cuda.Stream()
+        self.keep = []
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+
+
+_SINK = None
+
+
+def set_wgrad_sink(sink):
+    """Install (or remove with None) the side-stream weight-gradient sink; returns the previous one."""
+    global _SINK
+    prev, _SINK = _SINK, sink
+    return prev
+
+
+def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight=None, bias=None):
     """Shared by every contraction: g = gradient w.r.t. the pre-activation conv output."""
     taps, N, K = w_taps.shape
     dx = dw = db = None
+    sink = _SINK
+    if sink is not None and (needs_w or needs_b) and weight is not None and weight.is_leaf and weight.grad is not None and (
+            not needs_b or (bias is not None and bias.is_leaf and bias.grad is not None)):
+        sink.stream.wait_stream(torch.cuda.current_stream())  # g and x are complete on the main stream
+        sink.keep.append((g, x))
+        with torch.cuda.stream(sink.stream), ops.backward_precision():
+            if needs_b:
+                bias.grad.add_(ops.colsum(g))
+            if needs_w:
+                weight.grad.add_(ops.gemm_wgrad(g, x, taps, pad, conv_layout))
+        needs_w = needs_b = False
     if needs_b:
         db = ops.colsum(g)
     with ops.backward_precision():
@@ -111,6 +150,7 @@ class _Gemm(torch.autograd.Function):
                 aux = y
         ctx.save_for_backward(x, w_taps, aux)
         ctx.meta = (act, alpha, pad, conv_layout, bias is not None, residual is not None)
+        ctx.params = (weight, bias)
         return y
 
     @staticmethod
@@ -121,7 +161,7 @@ class _Gemm(torch.autograd.Function):
         g = g.contiguous()
         gz = g if (act is None and alpha == 1.0) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2])
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params)
         return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None, None
 
 
@@ -153,6 +193,7 @@ class _ConvBnAct(torch.autograd.Function):
         y = ops.affine_act(z, scale, shift, act, None, p, seed)  # BatchNorm affine + act + Dropout in one launch
         ctx.save_for_backward(x, w_taps, z, scale, shift, mean, rstd)
         ctx.meta = (act, training, pad, bias is not None, p, seed)
+        ctx.params = (weight, bias)
         return y
 
     @staticmethod
@@ -162,7 +203,7 @@ class _ConvBnAct(torch.autograd.Function):
         act, training, pad, has_bias, p, seed = ctx.meta
         gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training, p, seed)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, True, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2])
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params)
         return dx, dw, db, dgamma, dbeta, None, None, None, None
 
 

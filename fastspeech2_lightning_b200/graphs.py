@@ -80,20 +80,35 @@ class GraphedTrainStep:
     are never re-padded to share a graph.  The loss weights that depend on the epoch are part of the key.
     """
 
-    def __init__(self, model, optimizer, scheduler=None, max_graphs: int = 16):
+    def __init__(self, model, optimizer, scheduler=None, max_graphs: int = 16, overlap_wgrad: bool = True):
         self.model, self.opt, self.sched = model, optimizer, scheduler
         self.max_graphs = max_graphs
         self._cache: dict = {}
         self._seen: set = set()
         self._pool = None
+        self.overlap_wgrad = overlap_wgrad
+        self._sink = None
         lib().fs2k_set_dropout_seed_base(optimizer.seed_base.data_ptr())
 
     def _step_body(self, batch):
+        from . import autograd_fns as fns
+
         model, opt = self.model, self.opt
         opt.zero_grad()
         out = model(batch)
         losses = model.loss(out, batch, model.current_epoch)
-        losses["total"].backward()
+        if self.overlap_wgrad:
+            # weight / bias gradients of every contraction run on a second stream, straight into the flat gradient
+            if self._sink is None:
+                self._sink = fns.WgradSink()
+            prev = fns.set_wgrad_sink(self._sink)
+            try:
+                losses["total"].backward()
+            finally:
+                fns.set_wgrad_sink(prev)
+                self._sink.join()
+        else:
+            losses["total"].backward()
         opt.step()
         # detached: a loss that kept its autograd graph alive would also keep this step's AccumulateGrad nodes (and
         # their stream) alive into the next capture

@@ -149,3 +149,25 @@ def test_graph_replay_draws_fresh_dropout_masks_and_learning_rates():
     model.optimization_step(batch)
     moved = float((model.optimizer.flat_p - before).abs().max())
     assert 0 < moved <= 1.01 * lr_now * 1.5, (moved, lr_now)  # |Δp| ≤ lr·|m̂/√v̂| — bounded by ≈ lr early in training
+
+
+def test_side_stream_weight_gradients_equal_autograd_accumulated_ones():
+    """WgradSink: wgrad + bias column sums on a second stream, accumulated straight into the flat gradient buffer,
+    must leave exactly the gradient autograd's AccumulateGrad path leaves."""
+    from fastspeech2_lightning_b200.graphs import GraphedTrainStep
+
+    meta, _ = load_case("train_bn")
+    batch = case_batch(meta, DEV)
+    flat = {}
+    for overlap in (False, True):
+        model = _fresh_model(meta, clip=None)
+        for g in model.optimizer.param_groups:
+            g["lr"] = 0.0
+        model._train_runner = GraphedTrainStep(model, model.optimizer, None, overlap_wgrad=overlap)
+        model._train_runner._step_body(batch)
+        torch.cuda.synchronize()
+        flat[overlap] = model.optimizer.flat_g.clone()
+    assert float(flat[False].abs().max()) > 0
+    diff = (flat[False] - flat[True]).abs()
+    scale = float(flat[False].abs().max())
+    assert float(diff.max()) <= 1e-6 * scale, (float(diff.max()), scale, int((diff > 0).sum()))
