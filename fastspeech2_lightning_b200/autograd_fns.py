@@ -110,9 +110,9 @@ def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, we
         sink.keep.append((g, x))
         with torch.cuda.stream(sink.stream), ops.backward_precision():
             if needs_b:
-                bias.grad.add_(ops.colsum(g))
+                ops.colsum(g, out=bias.grad, accumulate=True)
             if needs_w:
-                weight.grad.add_(ops.gemm_wgrad(g, x, taps, pad, conv_layout))
+                ops.gemm_wgrad(g, x, taps, pad, conv_layout, accumulate_into=weight.grad)
         needs_w = needs_b = False
     if needs_b:
         db = ops.colsum(g)
@@ -563,7 +563,25 @@ class _CtcForwardSum(torch.autograd.Function):
 
 
 def ctc_forward_sum(attn_logprob, key_lens, query_lens, blank_logprob=-1.0):
+    pre = getattr(attn_logprob, "_fs2k_ctc", None)
+    if pre is not None and pre[2] == float(blank_logprob) and pre[3] is key_lens and pre[4] is query_lens:
+        torch.cuda.current_stream().wait_stream(pre[1])  # started early on the side stream (ctc_forward_sum_prefetch)
+        return pre[0]
     return _CtcForwardSum.apply(attn_logprob.contiguous(), key_lens, query_lens, float(blank_logprob))
+
+
+def ctc_forward_sum_prefetch(attn_logprob, key_lens, query_lens, blank_logprob=-1.0):
+    """With a WgradSink installed: start the forward-sum loss on the side stream as soon as the aligner has produced
+    attn_logprob.  Its sequential recursion (one CTA per utterance, F dependent steps) then overlaps the encoder /
+    decoder forward, and — autograd runs a node's backward on its forward's stream — its backward overlaps the
+    decoder backward.  The loss module picks the result up from the tensor (`ctc_forward_sum`)."""
+    sink = _SINK
+    if sink is None or not torch.is_grad_enabled() or not attn_logprob.requires_grad:
+        return
+    sink.stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(sink.stream):
+        loss = _CtcForwardSum.apply(attn_logprob.contiguous(), key_lens, query_lens, float(blank_logprob))
+    attn_logprob._fs2k_ctc = (loss, sink.stream, float(blank_logprob), key_lens, query_lens)
 
 
 def tanh_row(table, index):

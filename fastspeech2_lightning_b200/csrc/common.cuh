@@ -20,6 +20,18 @@ int fs2k_set_cuda_error(cudaError_t e);
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// grid of the column-reduction kernels (colsum / colstats / bn_bwd_stats): blockIdx.y = 128-channel block,
+// blockIdx.x = row chunk, ≈ 4 CTAs per SM in total, at least 32 rows per CTA
+static inline dim3 col_reduce_grid(long M, int C, long* rows_per_cta) {
+    const int cb = cdiv(C, 128);
+    long target = (148L * 4 + cb - 1) / cb;
+    long rows = (M + target - 1) / target;
+    if (rows < 32) rows = 32;
+    rows = (rows + 7) / 8 * 8;
+    *rows_per_cta = rows;
+    return dim3((unsigned)((M + rows - 1) / rows), (unsigned)cb);
+}
+
 namespace fs2k {
 
 constexpr int kWarp = 32;

@@ -44,16 +44,19 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
     }
 }
 
-// out[c] (+)= Σ_m z[m,c]   (out zeroed by the launcher; fp32 partials per CTA, one atomic per column per CTA)
+// out[c] += Σ_m z[m,c]   (out zeroed by the launcher unless it accumulates; fp32 partials per CTA, one atomic per
+// column per CTA; blockIdx.y selects the 128-channel block, blockIdx.x the row chunk)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, float* __restrict__ out) {
     __shared__ float s_part[8][128];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-    for (int c0 = 0; c0 < C; c0 += 128) {
+    {
+        const int c0 = blockIdx.y * 128;
         const int c = c0 + lane * 4;
         float s[4] = {0, 0, 0, 0};
         if (c < C)
+#pragma unroll 4
             for (long m = m0 + grp; m < m1; m += 8) {
                 const float4 v = *reinterpret_cast<const float4*>(z + (size_t)m * C + c);
                 s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
@@ -177,19 +180,19 @@ extern "C" int fs2k_act_bwd(const float* g, const float* aux, int mode, float al
     return FS2K_OK;
 }
 
-extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, fs2k_stream_t stream) {
+extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, int accumulate, fs2k_stream_t stream) {
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(z && out, FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * C, s);
-    if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * C, s);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    }
     if (M == 0) return FS2K_OK;
-    long ctas = (M + 127) / 128;
-    if (ctas > 148 * 2) ctas = 148 * 2;
-    const long rows = (M + ctas - 1) / ctas;
-    ctas = (M + rows - 1) / rows;
-    colsum_kernel<<<(int)ctas, 256, 0, s>>>(z, M, C, rows, out);
+    long rows;
+    const dim3 grid = col_reduce_grid(M, C, &rows);
+    colsum_kernel<<<grid, 256, 0, s>>>(z, M, C, rows, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -148,17 +148,47 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     }
 }
 
-// out (parameter layout: [N][K][taps] or [N][K]) = Σ_split ws[split][tap][n][k], fixed summation order
+// out (parameter layout: [N][K][taps] or [N][K]) (+)= Σ_split ws[split][tap][n][k], fixed summation order.
+// CTA = 32 float4 lanes × 8 split lanes: every thread sums its share of the splits (independent 16-byte loads), the
+// eight partial sums are added in lane order through shared memory.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int N, int K, float* __restrict__ out) {
-    const long total = (long)N * K * taps, plane = total;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int t = (int)(i % taps);
-        const long nk = i / taps;  // n·K + k
-        const float* p = ws + (size_t)t * N * K + nk;
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * plane];
-        out[i] = s;
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int N, int K, int accumulate,
+                    float* __restrict__ out) {
+    __shared__ float4 s_part[8][32];
+    const long nk4 = ((long)N * K) >> 2, total4 = nk4 * taps, plane4 = total4;
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const long i4 = (long)blockIdx.x * 32 + lane;  // float4 index inside one split plane [tap][n][k]
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < total4) {
+        const float4* p = reinterpret_cast<const float4*>(ws) + i4;
+#pragma unroll 4
+        for (int sp = sl; sp < splits; sp += 8) {
+            const float4 v = p[(size_t)sp * plane4];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    s_part[sl][lane] = acc;
+    __syncthreads();
+    if (sl == 0 && i4 < total4) {
+#pragma unroll
+        for (int g = 1; g < 8; ++g) {
+            const float4 v = s_part[g][lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int t = (int)(i4 / nk4);
+        const long nk = (i4 - (long)t * nk4) << 2;  // n·K + k of the first of the four elements
+        if (taps == 1) {
+            float4* o = reinterpret_cast<float4*>(out) + i4;
+            if (accumulate) { const float4 c = *o; acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w; }
+            *o = acc;
+        } else {
+            const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float* o = out + (nk + e) * taps + t;
+                *o = accumulate ? *o + a[e] : a[e];
+            }
+        }
     }
 }
 
@@ -196,7 +226,7 @@ extern "C" size_t fs2k_gemm_wgrad_tc_workspace_bytes(int B, int L, int N, int K,
 
 extern "C" int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps,
                                   int pad, int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout,
-                                  fs2k_stream_t stream) {
+                                  int accumulate, fs2k_stream_t stream) {
     FS2K_REQUIRE(B > 0 && L > 0 && N > 0 && K > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(passes == 1 || passes == 3, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(fs2k_gemm_wgrad_tc_supported(N, K, ldg, ldx), FS2K_ERR_UNSUPPORTED);
@@ -235,10 +265,9 @@ extern "C" int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int l
         gemm_wgrad_tc_kernel<1><<<grid, WG_THREADS, smem, s>>>(tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
     }
     FS2K_CHECK_LAUNCH();
-    long total = (long)N * K * taps;
-    long g = (total + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
-    wgrad_reduce_kernel<<<(int)g, 256, 0, s>>>((const float*)workspace, splits, taps, N, K, dW_param_layout);
+    const long total4 = ((long)N * K * taps) >> 2;  // N % 128 == 0, so N·K is a multiple of 4
+    wgrad_reduce_kernel<<<(int)((total4 + 31) / 32), 256, 0, s>>>((const float*)workspace, splits, taps, N, K, accumulate,
+                                                                 dW_param_layout);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -78,12 +78,14 @@ colstats_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, d
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta;
     const long m1 = min(M, m0 + rows_per_cta);
-    for (int c0 = 0; c0 < C; c0 += 128) {
+    {
+        const int c0 = blockIdx.y * 128;  // blockIdx.y = 128-channel block, blockIdx.x = row chunk
         const int c = c0 + lane * 4;
         float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
         double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
         int n = 0;
         if (c < C) {
+#pragma unroll 4
             for (long m = m0 + grp; m < m1; m += 8) {
                 const float4 v = *reinterpret_cast<const float4*>(z + (size_t)m * C + c);
                 s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
@@ -208,11 +210,9 @@ extern "C" int fs2k_colstats(const float* z, long M, int C, double* sums /* [2*C
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (M == 0) return FS2K_OK;
-    long ctas = (M + 255) / 256;
-    if (ctas > 148 * 4) ctas = 148 * 4;
-    const long rows_per_cta = (M + ctas - 1) / ctas;
-    ctas = (M + rows_per_cta - 1) / rows_per_cta;
-    colstats_kernel<<<(int)ctas, 256, 0, s>>>(z, M, C, rows_per_cta, sums);
+    long rows_per_cta;
+    const dim3 grid = col_reduce_grid(M, C, &rows_per_cta);
+    colstats_kernel<<<grid, 256, 0, s>>>(z, M, C, rows_per_cta, sums);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -107,7 +107,8 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
     __shared__ double s_part[8][128][2];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-    for (int c0 = 0; c0 < C; c0 += 128) {
+    {
+        const int c0 = blockIdx.y * 128;  // blockIdx.y = 128-channel block, blockIdx.x = row chunk
         const int c = c0 + lane * 4;
         double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
         if (c < C) {
@@ -116,6 +117,7 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
             for (int k = 0; k < 4; ++k) { sc[k] = scale[c + k]; sh[k] = shift[c + k]; mu[k] = mean[c + k]; rs[k] = rstd[c + k]; }
             float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
             int n = 0;
+#pragma unroll 2
             for (long m = m0 + grp; m < m1; m += 8) {
                 const float4 gv4 = *reinterpret_cast<const float4*>(g + (size_t)m * C + c);
                 const float4 zv4 = *reinterpret_cast<const float4*>(z + (size_t)m * C + c);
@@ -229,11 +231,9 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (M == 0) return FS2K_OK;
-    long ctas = (M + 255) / 256;
-    if (ctas > 148 * 4) ctas = 148 * 4;
-    const long rows = (M + ctas - 1) / ctas;
-    ctas = (M + rows - 1) / rows;
-    bn_bwd_stats_kernel<<<(int)ctas, 256, 0, s>>>(g, z, scale, shift, mean, rstd, act, M, C, rows, dropout_p, useed, sums);
+    long rows;
+    const dim3 sgrid = col_reduce_grid(M, C, &rows);
+    bn_bwd_stats_kernel<<<sgrid, 256, 0, s>>>(g, z, scale, shift, mean, rstd, act, M, C, rows, dropout_p, useed, sums);
     FS2K_CHECK_LAUNCH();
     long grid = (M * (C >> 2) + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;

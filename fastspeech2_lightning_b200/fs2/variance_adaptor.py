@@ -156,6 +156,8 @@ class VarianceAdaptor(nn.Module):
         if (teacher_forcing or not inference) and cfgm.learn_alignment:  # :248-305
             attn_soft, attn_logprob = self.attention.forward_blc(
                 batch["mel"], text_emb, mask=src_mask, key_lens=batch["src_lens"], attn_prior=batch["duration"])
+            if not inference:  # the forward-sum loss only needs attn_logprob: start it now, off the critical path
+                fns.ctc_forward_sum_prefetch(attn_logprob, batch["src_lens"], batch["mel_lens"])
             with torch.no_grad():
                 path, duration_target, attn_hard = ops.mas(attn_soft.detach(), batch["src_lens"], batch["mel_lens"],
                                                            take_log=True, dense=True)

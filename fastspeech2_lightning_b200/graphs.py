@@ -95,19 +95,22 @@ class GraphedTrainStep:
 
         model, opt = self.model, self.opt
         opt.zero_grad()
-        out = model(batch)
-        losses = model.loss(out, batch, model.current_epoch)
         if self.overlap_wgrad:
-            # weight / bias gradients of every contraction run on a second stream, straight into the flat gradient
+            # second stream: the forward-sum loss (started right after the aligner) and, in the backward, the weight /
+            # bias gradients of every contraction, accumulated straight into the flat gradient
             if self._sink is None:
                 self._sink = fns.WgradSink()
             prev = fns.set_wgrad_sink(self._sink)
             try:
+                out = model(batch)
+                losses = model.loss(out, batch, model.current_epoch)
                 losses["total"].backward()
             finally:
                 fns.set_wgrad_sink(prev)
                 self._sink.join()
         else:
+            out = model(batch)
+            losses = model.loss(out, batch, model.current_epoch)
             losses["total"].backward()
         opt.step()
         # detached: a loss that kept its autograd graph alive would also keep this step's AccumulateGrad nodes (and

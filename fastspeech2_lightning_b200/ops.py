@@ -576,11 +576,14 @@ def act_bwd(g, aux, act, alpha: float = 1.0, row_mask=None, dropout_p: float = 0
     return gz
 
 
-def colsum(z):
+def colsum(z, out=None, accumulate: bool = False):
+    """out[c] (+)= Σ_m z[m,c]  (bias gradients); `out` + `accumulate` add straight into an existing gradient."""
     z = _f32(z, "z")
     C = z.shape[-1]
-    out = torch.empty((C,), dtype=torch.float32, device=z.device)
-    check(lib().fs2k_colsum(_p(z), z.numel() // C, C, _p(out), _stream()), "fs2k_colsum")
+    if out is None:
+        out, accumulate = torch.empty((C,), dtype=torch.float32, device=z.device), False
+    assert out.is_contiguous() and out.numel() == C and out.dtype == torch.float32
+    check(lib().fs2k_colsum(_p(z), z.numel() // C, C, _p(out), int(accumulate), _stream()), "fs2k_colsum")
     _count()
     return out
 
@@ -595,8 +598,9 @@ def weight_taps_transposed(w_taps):
     return out
 
 
-def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool):
-    """dW for y = conv(x, W): g [B,L,N], x [B,L,K] → [N,K,taps] (conv_layout) or [N,K]."""
+def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=None):
+    """dW for y = conv(x, W): g [B,L,N], x [B,L,K] → [N,K,taps] (conv_layout) or [N,K].  `accumulate_into` (a
+    contiguous fp32 tensor of that shape, e.g. the parameter's .grad) receives `+= dW` instead of a new tensor."""
     g, x = _f32(g, "g"), _f32(x, "x")
     if g.dim() == 2:
         B, L = 1, g.shape[0]
@@ -607,21 +611,28 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool):
         # tensor cores (tcgen05, MN-major operands); the kernel writes the parameter layout directly
         ws_bytes = lib().fs2k_gemm_wgrad_tc_workspace_bytes(B, L, N, K, taps)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
-        out = torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
+        acc = accumulate_into is not None and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
+        out = accumulate_into if acc else torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
+        assert out.numel() == N * K * taps
         check(lib().fs2k_gemm_wgrad_tc(_p(g), N, _p(x), K, B, L, N, K, taps, pad, 3 if PRECISION == "tf32x3" else 1,
-                                       _p(ws), ws_bytes, _p(out), _stream()), "fs2k_gemm_wgrad_tc")
+                                       _p(ws), ws_bytes, _p(out), int(acc), _stream()), "fs2k_gemm_wgrad_tc")
         _count(2)
+        if accumulate_into is not None and not acc:
+            accumulate_into.add_(out)
         return out
     dw = torch.empty((taps, N, K), dtype=torch.float32, device=g.device)
     check(lib().fs2k_gemm_wgrad(_p(g), N, _p(x), K, B, L, N, K, taps, pad, _p(dw), _stream()), "fs2k_gemm_wgrad")
     _count()
     if not conv_layout:
-        return dw[0]
-    if taps == 1:
-        return dw.reshape(N, K, 1)
-    out = torch.empty((N, K, taps), dtype=torch.float32, device=g.device)
-    check(lib().fs2k_unpack_conv_weight(_p(dw), N, K, taps, _p(out), _stream()), "fs2k_unpack_conv_weight")
-    _count()
+        out = dw[0]
+    elif taps == 1:
+        out = dw.reshape(N, K, 1)
+    else:
+        out = torch.empty((N, K, taps), dtype=torch.float32, device=g.device)
+        check(lib().fs2k_unpack_conv_weight(_p(dw), N, K, taps, _p(out), _stream()), "fs2k_unpack_conv_weight")
+        _count()
+    if accumulate_into is not None:
+        accumulate_into.add_(out)
     return out
 
 

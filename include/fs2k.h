@@ -191,7 +191,7 @@ int fs2k_ctc_forward_sum_bwd(const float* attn_logprob, const double* lse, const
  * gemm_wgrad: dW[tap][n][k] = Σ_(b,l) G[b,l,n] · X[b,l+tap-pad,k]  (dW zeroed here, split over rows + atomics). */
 int fs2k_act_bwd(const float* g, const float* aux, int mode, float alpha, const uint8_t* row_mask, long M, int C,
                  float dropout_p, long seed, float* gz, fs2k_stream_t stream);
-int fs2k_colsum(const float* z, long M, int C, float* out, fs2k_stream_t stream);
+int fs2k_colsum(const float* z, long M, int C, float* out, int accumulate, fs2k_stream_t stream);
 int fs2k_repack_weight_t(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
 int fs2k_unpack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);
 int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
@@ -203,7 +203,8 @@ int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx, int B, int
 int fs2k_gemm_wgrad_tc_supported(int N, int K, int ldg, int ldx);
 size_t fs2k_gemm_wgrad_tc_workspace_bytes(int B, int L, int N, int K, int taps);
 int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
-                       int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout, fs2k_stream_t stream);
+                       int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout, int accumulate,
+                       fs2k_stream_t stream);
 /* LayerNorm backward (dgamma/dbeta zeroed here, accumulated with atomics) */
 int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                        long M, int D, float dropout_p, long seed, float* dx, float* dgamma, float* dbeta,

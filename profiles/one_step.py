@@ -20,10 +20,7 @@ if wl["kind"] == "train":
     batch = synthetic.batch_to(bench.make_train_batches(wl, 1, 0)[0], dev)
 
     def step():
-        opt.zero_grad()
-        out = model(batch)
-        model.loss(out, batch, 0)["total"].backward()
-        opt.step()
+        model.optimization_step(batch, use_cuda_graph=False)  # eager launches, wgrad on the side stream
 else:
     cfg, model = bench.build_model(wl, dev)
     batch = synthetic.batch_to(bench.make_batches(wl, 1, 0)[0], dev)
