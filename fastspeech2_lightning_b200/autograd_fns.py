@@ -141,7 +141,10 @@ class _Gemm(torch.autograd.Function):
             if alpha != 1.0:
                 raise NotImplementedError("alpha with silu")
         elif p:
-            raise NotImplementedError("fused dropout is only wired for the SiLU epilogue")
+            # residual + Dropout(Linear(x))·alpha in the GEMM epilogue; the backward regenerates the mask in act_bwd
+            if act is not None:
+                raise NotImplementedError("fused dropout is wired for the SiLU and the plain epilogue")
+            y = ops.gemm(x, w_taps, bias, taps_pad=pad, alpha=alpha, residual=residual, dropout_p=p, seed=seed)
         else:
             y = ops.gemm(x, w_taps, bias, taps_pad=pad, act=act, alpha=alpha, residual=residual)
             if act in ("relu", "tanh"):
@@ -159,7 +162,7 @@ class _Gemm(torch.autograd.Function):
         x, w_taps, aux = ctx.saved_tensors
         act, alpha, pad, conv_layout, has_bias, has_res = ctx.meta
         g = g.contiguous()
-        gz = g if (act is None and alpha == 1.0) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
+        gz = g if (act is None and alpha == 1.0 and not ctx.drop[0]) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                     has_bias and ctx.needs_input_grad[2], *ctx.params)
         return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None, None
@@ -168,8 +171,10 @@ class _Gemm(torch.autograd.Function):
 def linear(x, weight, bias, act, alpha, residual, dropout_p=0.0):
     if dropout_p and act == "silu" and residual is None:
         return _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha, float(dropout_p))
+    if dropout_p and act is None:
+        # reference order: residual + Dropout(Linear(...))·alpha — all of it in the GEMM epilogue
+        return _Gemm.apply(x.contiguous(), weight, bias, residual, None, alpha, float(dropout_p))
     if dropout_p:
-        # reference order: residual + Dropout(Linear(...)·alpha): GEMM, then dropout + residual add in one launch
         y = _Gemm.apply(x.contiguous(), weight, bias, None, act, alpha, 0.0)
         return dropout(y, dropout_p, residual)
     return _Gemm.apply(x.contiguous(), weight, bias, residual, act, alpha, 0.0)

@@ -1,7 +1,7 @@
 // Tensor-core GEMM / 1-D convolution for sm_100a: TMA → shared memory → tcgen05.mma (kind::tf32,
 // accumulators in TMEM) → fused epilogue.  Same contract as fs2k_gemm_f32 (gemm_simt.cu):
 //
-//   C[(b,l), n] = (act((Σ_tap Σ_k A[b, l+tap−pad, k] · W[tap][n][k] + bias[n])·scale[n] + shift[n])·alpha
+//   C[(b,l), n] = (dropout(act((Σ_tap Σ_k A[b, l+tap−pad, k] · W[tap][n][k] + bias[n])·scale[n] + shift[n])·alpha)
 //                 + residual[(b,l), n]) · row_mask[(b,l)]          (+ optional LayerNorm of the finished row)
 //
 // One 128 × BLOCK_N output tile per CTA (BLOCK_N = N when N ≤ 256, else 256).  Operands stay fp32 in
@@ -21,8 +21,14 @@
 namespace fs2k {
 
 constexpr int TC_BM = 128;      // rows per tile == TMEM lanes
-constexpr int TC_BK = 32;       // fp32 elements per 128-byte swizzle atom
-template <int PASSES> struct TcStages { static constexpr int value = PASSES == 3 ? 2 : 4; };  // 3×TF32 keeps a second copy of every tile
+// K elements per pipeline stage: 32 floats = one 128-byte swizzle atom per row.  3×TF32 keeps a second ("small")
+// copy of every tile, so a stage costs 96 KB and only two fit; the ring is then latency-bound (stage cycle = TMA
+// latency + split + MMA ≈ 2.7 µs against 0.85 µs of MMA work).  Half-width stages (16 floats, 64-byte swizzle —
+// set value = 16 below, the descriptors and tensor maps follow) give four stages in the same shared memory, but were
+// measured SLOWER (main loop 10.9 µs vs 9.7 µs at K = 256, N = 256): the per-stage fixed costs (barrier round trips,
+// splitter hand-off) do not shrink with the stage.
+template <int PASSES> struct TcBK { static constexpr int value = 32; };
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 384;
 
 struct TcEpilogue {
@@ -34,6 +40,7 @@ struct TcEpilogue {
     // optional fused LayerNorm of the finished row (requires BLOCK_N == N)
     const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_out; int ld_ln;
     const float* ln2_gamma; const float* ln2_beta; float* ln2_out;  // second LN chained on ln_out
+    float drop_p; unsigned long long seed;  // dropout of the value before the residual add (mask = hash(seed, m·N + n))
     unsigned long long* dbg;  // optional: 8 globaltimer stamps of CTA (0,0) (profiling aid, normally null)
 };
 __device__ __forceinline__ void tc_stamp(const TcEpilogue& ep, int slot) {
@@ -44,14 +51,17 @@ __device__ __forceinline__ void tc_stamp(const TcEpilogue& ep, int slot) {
     }
 }
 
-// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1
+// K-major operand whose rows are one swizzle atom wide (BK·4 = 128 or 64 bytes): 8-row groups are 8·row bytes apart
+// (SBO), descriptor version 1, layout type SWIZZLE_128B (2) or SWIZZLE_64B (4)
+template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    static_assert(BK == 32 || BK == 16, "row = one 128-byte or 64-byte swizzle atom");
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;         // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;          // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n
@@ -98,8 +108,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
                TcEpilogue ep) {
     extern __shared__ uint8_t smem_raw[];
-    const int TC_STAGES = n_stages;  // 2..4, as many as fit next to the staging tile (host decides)
-    __shared__ __align__(8) uint64_t s_full[4], s_empty[4], s_split[4], s_tmem_full;
+    constexpr int TC_BK = TcBK<PASSES>::value;
+    const int TC_STAGES = n_stages;  // 2..8, as many as fit in shared memory (host decides)
+    __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_split[TC_MAX_STAGES], s_tmem_full;
     __shared__ uint32_t s_tmem_base;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -159,11 +170,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t ad = make_smem_desc(sa + k * 32), bd = make_smem_desc(sb + k * 32);
+                    const uint64_t ad = make_smem_desc<TC_BK>(sa + k * 32), bd = make_smem_desc<TC_BK>(sb + k * 32);
                     tc_mma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
                     if (PASSES == 3) {
-                        const uint64_t ads = make_smem_desc(sa + a_bytes + b_bytes + k * 32);
-                        const uint64_t bds = make_smem_desc(sb + a_bytes + b_bytes + k * 32);
+                        const uint64_t ads = make_smem_desc<TC_BK>(sa + a_bytes + b_bytes + k * 32);
+                        const uint64_t bds = make_smem_desc<TC_BK>(sb + a_bytes + b_bytes + k * 32);
                         tc_mma_tf32(tmem_base, ad, bds, idesc, 1u);
                         tc_mma_tf32(tmem_base, ads, bd, idesc, 1u);
                     }
@@ -229,6 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int rows_valid = (int)min((long)TC_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
         const float inv_n = 1.0f / (float)block_n;
+        const float drop_p = ep.drop_p, inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+        const unsigned long long seed = drop_p > 0.f ? seed_with_base(ep.seed) : 0ull;
         for (int rb = warp; rb < rows_valid; rb += TC_WARPS * TC_ROWS_PER_ITER) {
             float4 val[TC_ROWS_PER_ITER][2], res[TC_ROWS_PER_ITER][2];
             float rm[TC_ROWS_PER_ITER];
@@ -258,6 +271,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int qv = lane + 32 * j;
                         float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
                         v = tc_colmath(v, bias4[j], sc4[j], sh4[j], ep.act, ep.alpha);
+                        if (drop_p > 0.f) {
+                            const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
+                            v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
+                            v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
+                            v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
+                            v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                        }
                         v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
                         v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];
                         if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
@@ -329,10 +349,11 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
                             const float* bias, const float* scale, const float* shift, int act, float alpha,
                             const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
                             const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
-                            const float* ln2_gamma, const float* ln2_beta, float* ln2_out, int passes,
-                            fs2k_stream_t stream) {
+                            const float* ln2_gamma, const float* ln2_beta, float* ln2_out, float dropout_p, long seed,
+                            int passes, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && K > 0 && N > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(act >= 0 && act <= 3 && (passes == 1 || passes == 3), FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(fs2k_gemm_tc_supported(K, N, lda, taps), FS2K_ERR_UNSUPPORTED);
     const long M = (long)B * L;
     if (M == 0) return FS2K_OK;
@@ -360,32 +381,36 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     FS2K_REQUIRE(Lm < (1L << 31), FS2K_ERR_UNSUPPORTED);
     const int tiles_per_b = (int)((Lm + TC_BM - 1) / TC_BM);
 
+    const int bk = passes == 3 ? TcBK<3>::value : TcBK<1>::value;
+    const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Lm, (cuuint64_t)Bm};
         cuuint64_t strides[2] = {(cuuint64_t)lda * 4, (cuuint64_t)Lm * lda * 4};
-        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        cuuint32_t box[3] = {(cuuint32_t)bk, TC_BM, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)A, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)taps * N};
         cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-        cuuint32_t box[2] = {TC_BK, (cuuint32_t)block_n};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
     }
     TcEpilogue ep{bias, scale, shift, act, alpha, residual, ldr, row_mask, C, ldc,
-                  ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out, g_tc_debug_stamps};
-    const size_t stage = (size_t)(TC_BM + block_n) * TC_BK * 4 * (passes == 3 ? 2 : 1);
+                  ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out, dropout_p, (unsigned long long)seed,
+                  g_tc_debug_stamps};
+    const size_t stage = (size_t)(TC_BM + block_n) * bk * 4 * (passes == 3 ? 2 : 1);
     int n_stages = (int)((226 * 1024) / stage);
-    if (n_stages > 4) n_stages = 4;
+    const int max_stages = passes == 3 ? TC_MAX_STAGES : 4;
+    if (n_stages > max_stages) n_stages = max_stages;
     FS2K_REQUIRE(n_stages >= 2, FS2K_ERR_UNSUPPORTED);
     size_t smem = stage * n_stages;
     const size_t staging = (size_t)TC_BM * (block_n + 4) * 4;
@@ -407,3 +432,5 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
+
+FS2K_DEFINE_SEED_BASE_SETTER(gemm_tc)

@@ -311,16 +311,21 @@ class backward_precision:
 
 
 def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,
-         residual=None, row_mask=None, out=None, ln=None, ln2=None, want_c: bool = True):
+         residual=None, row_mask=None, out=None, ln=None, ln2=None, want_c: bool = True, dropout_p: float = 0.0,
+         seed: int = 0):
     """a [B,L,K] (or [M,K]) · w [taps,N,K] or [N,K] with the fused epilogue of fs2k_gemm_{tc,f32}.
 
     ln = (gamma, beta, eps): also return LayerNorm(result) — fused into the tensor-core epilogue when one
     tile spans the row, otherwise a separate fs2k_layernorm_fwd launch; ln2 = (gamma, beta) chains a second
     LayerNorm on the first one's output.  Returns C, or (C, ln_out[, ln2_out]) when ln is given."""
     if ln is not None or PRECISION != "fp32":
-        r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c)
+        r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p, seed)
         if r is not None:
             return r
+    if dropout_p:  # SIMT fallback: dropout(+residual) as its own launch
+        assert ln is None and row_mask is None
+        c = _gemm_f32(a, w, bias, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha)
+        return dropout(c, dropout_p, seed, residual)
     c = _gemm_f32(a, w, bias, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha, residual=residual,
                   row_mask=row_mask, out=out)
     if ln is None:
@@ -331,7 +336,7 @@ def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None
     return c, y, layernorm(y, ln2[0], ln2[1], ln[2])
 
 
-def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c):
+def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p=0.0, seed=0):
     if PRECISION == "fp32":
         return None
     a = _f32(a, "a")
@@ -361,7 +366,7 @@ def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask,
                              float(alpha), _p(residual), N, _p(row_mask), _p(c), N,
                              _p(ln[0]) if fuse_ln else None, _p(ln[1]) if fuse_ln else None, float(ln[2]) if fuse_ln else 0.0,
                              _p(ln_out), _p(ln2[0]) if ln2_out is not None else None, _p(ln2[1]) if ln2_out is not None else None,
-                             _p(ln2_out), 3 if PRECISION == "tf32x3" else 1, _stream()), "fs2k_gemm_tc")
+                             _p(ln2_out), float(dropout_p), int(seed), 3 if PRECISION == "tf32x3" else 1, _stream()), "fs2k_gemm_tc")
     _count()
     if ln is None:
         return c
