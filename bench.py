@@ -625,7 +625,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # NCCL communicators that were captured into CUDA graphs do not tear down reliably (destroy_process_group
+        # was seen to hang after the result was printed): drain the device, meet the other ranks, leave at once.
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
