@@ -7,6 +7,7 @@ from `include/fs2k.h`, so the header is the single source of truth for the C ABI
 from __future__ import annotations
 
 import ctypes
+import os
 import re
 import shutil
 from pathlib import Path
@@ -122,6 +123,8 @@ def lib():
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = cdll
+    if os.environ.get("FS2K_PDL", "1") == "0":  # plain launches (no programmatic dependent launch), for A/B timing
+        cdll.fs2k_set_pdl(0)
     return cdll
 
 

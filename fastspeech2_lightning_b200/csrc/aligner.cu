@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256)
 aligner_dist_kernel(const float* __restrict__ q,  // [B,F,C]
                     const float* __restrict__ k,  // [B,T,C]
                     int F, int T, int C, float coef, float* __restrict__ dist /* [B,F,T] */) {
+    pdl_prologue();
     __shared__ __align__(16) float Qs[DT][CCH + 4];
     __shared__ __align__(16) float Ks[DT][CCH + 4];
     const int b = blockIdx.z, f0 = blockIdx.y * DT, t0 = blockIdx.x * DT;
@@ -72,6 +73,7 @@ aligner_softmax_kernel(const float* dist,   // [B,F,T] raw scores (may alias `so
                        const float* __restrict__ prior,  // [B,F,T] or null
                        const int* __restrict__ key_lens, // [B] or null (no key mask)
                        int B, int F, int T, float* __restrict__ logprob, float* soft) {
+    pdl_prologue();
     extern __shared__ float rows[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* r = rows + (size_t)warp * T;
@@ -127,7 +129,7 @@ extern "C" int fs2k_aligner_fwd(const float* q, const float* k, const float* pri
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(cdiv(T, DT), cdiv(F, DT), B);
     // raw scores are staged in `soft` (overwritten by the normalisation pass, row by row, after it is read)
-    aligner_dist_kernel<80><<<grid, 256, 0, s>>>(q, k, F, T, C, -0.0005f, soft);
+    fs2k_launch(aligner_dist_kernel<80>, dim3(grid), dim3(256), 0, s, q, k, F, T, C, -0.0005f, soft);
     FS2K_CHECK_LAUNCH();
     const int smem = 4 * T * (int)sizeof(float);
     if (smem > 48 * 1024) {
@@ -136,7 +138,7 @@ extern "C" int fs2k_aligner_fwd(const float* q, const float* k, const float* pri
     }
     long g = ((long)B * F + 3) / 4;
     if (g > 148 * 16) g = 148 * 16;
-    aligner_softmax_kernel<<<(int)g, 128, smem, s>>>(soft, prior, key_lens, B, F, T, logprob, soft);
+    fs2k_launch(aligner_softmax_kernel, dim3((int)g), dim3(128), smem, s, soft, prior, key_lens, B, F, T, logprob, soft);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -14,6 +14,7 @@ namespace fs2k {
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ dO, int B, int L, int H, int HD,
                   float* __restrict__ delta) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const long n = (long)B * L * H;
     for (long i = (long)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (long)gridDim.x * 8) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                    const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
                    float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int BQ = 64, BKEY = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                     const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
                     float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int BKEY = 64, BQ = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
@@ -301,7 +304,7 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
     const float scale = 1.0f / sqrtf((float)head_dim);
     long g = ((long)B * L * H + 7) / 8;
     if (g > 148 * 8) g = 148 * 8;
-    attn_delta_kernel<<<(int)g, 256, 0, s>>>(out, dout, B, L, H, head_dim, delta);
+    fs2k_launch(attn_delta_kernel, dim3((int)g), dim3(256), 0, s, out, dout, B, L, H, head_dim, delta);
     FS2K_CHECK_LAUNCH();
     const int QS = head_dim + 4;
     const int smem_dq = ((64 + 64 + 32 + 32) * QS + 64 * 36) * 4;
@@ -311,16 +314,16 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
         e = cudaFuncSetAttribute(attn_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        attn_bwd_dq_kernel<128><<<dim3(cdiv(L, 64), H, B), 256, smem_dq, s>>>(qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dq_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
         FS2K_CHECK_LAUNCH();
-        attn_bwd_dkv_kernel<128><<<dim3(cdiv(L, 64), H, B), 256, smem_dkv, s>>>(qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dkv_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
     } else {
         e = cudaFuncSetAttribute(attn_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        attn_bwd_dq_kernel<64><<<dim3(cdiv(L, 64), H, B), 256, smem_dq, s>>>(qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dq_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
         FS2K_CHECK_LAUNCH();
-        attn_bwd_dkv_kernel<64><<<dim3(cdiv(L, 64), H, B), 256, smem_dkv, s>>>(qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dkv_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -19,6 +19,7 @@ template <int HD>
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ lens, int L, int H, float scale,
                       float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ lse_out) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int QS = HD + 4, PS = ABK + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
@@ -179,10 +180,10 @@ extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int 
             if (e != cudaSuccess) return fs2k_set_cuda_error(e);
             set = true;
         }
-        attention_simt_kernel<128><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
+        fs2k_launch(attention_simt_kernel<128>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     } else {
         const int smem = (ABQ * 68 + ABK * 68 + ABK * 64 + ABQ * (ABK + 4)) * 4;
-        attention_simt_kernel<64><<<grid, 256, smem, s>>>(qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
+        fs2k_launch(attention_simt_kernel<64>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -18,6 +18,38 @@
 
 int fs2k_set_cuda_error(cudaError_t e);
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Every kernel of the library is launched through fs2k_launch with programmatic stream serialization allowed:
+// the next kernel of the stream (or the next kernel node of a captured graph) may be scheduled as soon as every
+// CTA of this one has executed griddepcontrol.launch_dependents — which every kernel does first thing — and
+// then blocks in griddepcontrol.wait until this grid has completed and its writes are visible.  Launch latency
+// and kernel prologues (barrier init, TMEM allocation, parameter loads) overlap the tail of the previous kernel;
+// nothing that reads or writes global memory runs before the wait.  fs2k_set_pdl(0) switches the attribute off.
+extern int g_fs2k_pdl_enabled;  // lib.cu
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+static inline void fs2k_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_fs2k_pdl_enabled ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in FS2K_CHECK_LAUNCH
+}
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // grid of the column-reduction kernels (colsum / colstats / bn_bwd_stats): blockIdx.y = 128-channel block,

@@ -8,6 +8,7 @@ namespace fs2k {
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, const float* __restrict__ residual, float p, float inv_keep,
                unsigned long long seed, long N, float* __restrict__ y) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const float v = hash_uniform(seed, (unsigned long long)i) >= p ? x[i] * inv_keep : 0.f;
@@ -24,7 +25,7 @@ extern "C" int fs2k_dropout(const float* x, const float* residual, float p, long
     FS2K_REQUIRE(x && y, FS2K_ERR_NULL);
     long g = (N + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    fs2k::dropout_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, residual, p, 1.0f / (1.0f - p), (unsigned long long)seed, N, y);
+    fs2k_launch(fs2k::dropout_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, x, residual, p, 1.0f / (1.0f - p), (unsigned long long)seed, N, y);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -24,6 +24,7 @@ dwconv_kernel(const float* __restrict__ x,  // [B,L,ldx]  (GLU: value at c, gate
               const float* __restrict__ scale, const float* __restrict__ shift,
               float* __restrict__ y)           // [B,L,C]
 {
+    pdl_prologue();
     constexpr int P = (K - 1) / 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.z;
@@ -71,11 +72,11 @@ static int launch_dw(const float* x, int ldx, int B, int L, int C, const float* 
     const int threads = C < 256 ? ((C + 31) / 32) * 32 : 256;
     grid.x = cdiv(C, threads);
     if (glu) {
-        if (scale) dwconv_kernel<K, true, 1><<<grid, threads, 0, s>>>(x, ldx, L, C, w, bias, scale, shift, y);
-        else dwconv_kernel<K, true, 0><<<grid, threads, 0, s>>>(x, ldx, L, C, w, bias, scale, shift, y);
+        if (scale) fs2k_launch(dwconv_kernel<K, true, 1>, dim3(grid), dim3(threads), 0, s, x, ldx, L, C, w, bias, scale, shift, y);
+        else fs2k_launch(dwconv_kernel<K, true, 0>, dim3(grid), dim3(threads), 0, s, x, ldx, L, C, w, bias, scale, shift, y);
     } else {
-        if (scale) dwconv_kernel<K, false, 1><<<grid, threads, 0, s>>>(x, ldx, L, C, w, bias, scale, shift, y);
-        else dwconv_kernel<K, false, 0><<<grid, threads, 0, s>>>(x, ldx, L, C, w, bias, scale, shift, y);
+        if (scale) fs2k_launch(dwconv_kernel<K, false, 1>, dim3(grid), dim3(threads), 0, s, x, ldx, L, C, w, bias, scale, shift, y);
+        else fs2k_launch(dwconv_kernel<K, false, 0>, dim3(grid), dim3(threads), 0, s, x, ldx, L, C, w, bias, scale, shift, y);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

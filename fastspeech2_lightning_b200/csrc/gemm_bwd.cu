@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int mode, float alpha,
                const uint8_t* __restrict__ row_mask, long M, int C, float drop_p, unsigned long long seed,
                float* __restrict__ gz) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
@@ -48,6 +49,7 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
 // column per CTA; blockIdx.y selects the 128-channel block, blockIdx.x the row chunk)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, float* __restrict__ out) {
+    pdl_prologue();
     __shared__ float s_part[8][128];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
@@ -76,6 +78,7 @@ colsum_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, flo
 
 // [taps][N][K] → [taps][K][N] with the taps reversed: the weights of the transposed convolution
 __global__ void repack_weight_t_kernel(const float* __restrict__ w, int N, int K, int taps, float* __restrict__ out) {
+    pdl_prologue();
     const long total = (long)N * K * taps;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int n = (int)(i % N);
@@ -87,6 +90,7 @@ __global__ void repack_weight_t_kernel(const float* __restrict__ w, int N, int K
 
 // [taps][N][K] → PyTorch Conv1d layout [N][K][taps]
 __global__ void unpack_conv_weight_kernel(const float* __restrict__ w, int N, int K, int taps, float* __restrict__ out) {
+    pdl_prologue();
     const long total = (long)N * K * taps;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int t = (int)(i % taps);
@@ -101,6 +105,7 @@ constexpr int WG_T = 64, WG_MK = 16;
 __global__ void __launch_bounds__(256)
 gemm_wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, int B, int L, int N,
                   int K, int taps, int pad, long rows_per_split, float* __restrict__ dW) {
+    pdl_prologue();
     __shared__ __align__(16) float Gs[WG_MK][WG_T + 4];
     __shared__ __align__(16) float Xs[WG_MK][WG_T + 4];
     const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
@@ -175,7 +180,7 @@ extern "C" int fs2k_act_bwd(const float* g, const float* aux, int mode, float al
     FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
     if (M == 0) return FS2K_OK;
     FS2K_REQUIRE(g && gz && (mode == 0 || aux), FS2K_ERR_NULL);
-    act_bwd_kernel<<<ew_grid2(M * (C >> 2)), 256, 0, (cudaStream_t)stream>>>(g, aux, mode, alpha, row_mask, M, C, dropout_p, (unsigned long long)seed, gz);
+    fs2k_launch(act_bwd_kernel, dim3(ew_grid2(M * (C >> 2))), dim3(256), 0, (cudaStream_t)stream, g, aux, mode, alpha, row_mask, M, C, dropout_p, (unsigned long long)seed, gz);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -192,7 +197,7 @@ extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, int accumu
     if (M == 0) return FS2K_OK;
     long rows;
     const dim3 grid = col_reduce_grid(M, C, &rows);
-    colsum_kernel<<<grid, 256, 0, s>>>(z, M, C, rows, out);
+    fs2k_launch(colsum_kernel, dim3(grid), dim3(256), 0, s, z, M, C, rows, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -200,7 +205,7 @@ extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, int accumu
 extern "C" int fs2k_repack_weight_t(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream) {
     FS2K_REQUIRE(N > 0 && K > 0 && taps > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(w && out, FS2K_ERR_NULL);
-    repack_weight_t_kernel<<<ew_grid2((long)N * K * taps), 256, 0, (cudaStream_t)stream>>>(w, N, K, taps, out);
+    fs2k_launch(repack_weight_t_kernel, dim3(ew_grid2((long)N * K * taps)), dim3(256), 0, (cudaStream_t)stream, w, N, K, taps, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -208,7 +213,7 @@ extern "C" int fs2k_repack_weight_t(const float* w, int N, int K, int taps, floa
 extern "C" int fs2k_unpack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream) {
     FS2K_REQUIRE(N > 0 && K > 0 && taps > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(w && out, FS2K_ERR_NULL);
-    unpack_conv_weight_kernel<<<ew_grid2((long)N * K * taps), 256, 0, (cudaStream_t)stream>>>(w, N, K, taps, out);
+    fs2k_launch(unpack_conv_weight_kernel, dim3(ew_grid2((long)N * K * taps)), dim3(256), 0, (cudaStream_t)stream, w, N, K, taps, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -232,7 +237,7 @@ extern "C" int fs2k_gemm_wgrad(const float* G, int ldg, const float* X, int ldx,
     splits = (M + rows - 1) / rows;
     FS2K_REQUIRE(splits * taps <= 65535, FS2K_ERR_UNSUPPORTED);
     dim3 grid(gx, gy, (unsigned)(splits * taps));
-    gemm_wgrad_kernel<<<grid, 256, 0, s>>>(G, ldg, X, ldx, B, L, N, K, taps, pad, rows, dW);
+    fs2k_launch(gemm_wgrad_kernel, dim3(grid), dim3(256), 0, s, G, ldg, X, ldx, B, L, N, K, taps, pad, rows, dW);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

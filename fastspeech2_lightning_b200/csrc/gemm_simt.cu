@@ -40,6 +40,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <bool KVEC>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const GemmArgs g) {
+    pdl_prologue();
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
     const int tid = threadIdx.x;
@@ -198,6 +199,7 @@ gemm_simt_kernel(const GemmArgs g) {
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
               const uint8_t* __restrict__ mask, long M, int D, float* __restrict__ y) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     for (long m = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M;
          m += (long)gridDim.x * (blockDim.x >> 5)) {
@@ -218,6 +220,7 @@ rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
 
 // Conv1d weight [N][K][taps] (PyTorch layout) → [taps][N][K] (k contiguous per tap)
 __global__ void repack_conv_weight_kernel(const float* __restrict__ w, int N, int K, int taps, float* __restrict__ out) {
+    pdl_prologue();
     const long total = (long)N * K * taps;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
@@ -244,8 +247,8 @@ extern "C" int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const
     GemmArgs g{A, lda, B, L, K, W, N, taps, pad, bias, scale, shift, act, alpha, residual, ldr, row_mask, C, ldc};
     dim3 grid(cdiv(M, BM), cdiv(N, BN));
     const bool kvec = (K & 3) == 0 && (lda & 3) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0;
-    if (kvec) gemm_simt_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
-    else gemm_simt_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+    if (kvec) fs2k_launch(gemm_simt_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g);
+    else fs2k_launch(gemm_simt_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -258,7 +261,7 @@ extern "C" int fs2k_rowdot(const float* x, const float* w, const float* b, const
     FS2K_REQUIRE(x && w && y, FS2K_ERR_NULL);
     long g = (M + 7) / 8;
     if (g > 148 * 8) g = 148 * 8;
-    rowdot_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, b, mask, M, D, y);
+    fs2k_launch(rowdot_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, x, w, b, mask, M, D, y);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -269,7 +272,7 @@ extern "C" int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, f
     long total = (long)N * K * taps;
     long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    repack_conv_weight_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, N, K, taps, out);
+    fs2k_launch(repack_conv_weight_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, w, N, K, taps, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
                TcEpilogue ep) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     constexpr int TC_BK = TcBK<PASSES>::value;
     const int TC_STAGES = n_stages;  // 2..8, as many as fit in shared memory (host decides)
@@ -142,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    pdl_wait();  // barrier init + TMEM allocation above overlapped the previous kernel's tail; memory is touched below
     if (threadIdx.x == 0) tc_stamp(ep, 1);
 
     if (warp == 0) {
@@ -423,11 +425,11 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     if (passes == 3) {
         e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
+        fs2k_launch(gemm_tc_kernel<3>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
     } else {
         e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
+        fs2k_launch(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, int L, int N,
                      int K, int tile_k, int taps, int pad, int chunks_per_b, int n_chunks, int chunks_per_split,
                      float* __restrict__ ws) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     constexpr int STAGES = WgStages<PASSES>::value;
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_split[STAGES], s_tmem_full;
@@ -68,6 +69,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    pdl_wait();  // setup above overlapped the previous kernel; global memory is touched from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -154,6 +156,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int N, int K, int accumulate,
                     float* __restrict__ out) {
+    pdl_prologue();
     __shared__ float4 s_part[8][32];
     const long nk4 = ((long)N * K) >> 2, total4 = nk4 * taps, plane4 = total4;
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -258,15 +261,15 @@ extern "C" int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int l
     if (passes == 3) {
         e = cudaFuncSetAttribute(gemm_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_wgrad_tc_kernel<3><<<grid, WG_THREADS, smem, s>>>(tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+        fs2k_launch(gemm_wgrad_tc_kernel<3>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
     } else {
         e = cudaFuncSetAttribute(gemm_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        gemm_wgrad_tc_kernel<1><<<grid, WG_THREADS, smem, s>>>(tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+        fs2k_launch(gemm_wgrad_tc_kernel<1>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
     }
     FS2K_CHECK_LAUNCH();
     const long total4 = ((long)N * K * taps) >> 2;  // N % 128 == 0, so N·K is a multiple of 4
-    wgrad_reduce_kernel<<<(int)((total4 + 31) / 32), 256, 0, s>>>((const float*)workspace, splits, taps, N, K, accumulate,
+    fs2k_launch(wgrad_reduce_kernel, dim3((int)((total4 + 31) / 32)), dim3(256), 0, s, (const float*)workspace, splits, taps, N, K, accumulate,
                                                                  dW_param_layout);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

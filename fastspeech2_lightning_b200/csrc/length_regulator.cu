@@ -16,6 +16,7 @@ namespace fs2k {
 // ---- scan: one warp per utterance, inclusive prefix sum of durations ----
 __global__ void __launch_bounds__(128)
 lr_scan_kernel(const int* __restrict__ dur, int B, int T, int* __restrict__ cum, int* __restrict__ total) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -51,6 +52,7 @@ lr_gather_kernel(const float* __restrict__ x,    // [B,T,D]
                  uint8_t* __restrict__ mask,     // [B,F_out] or null
                  int* __restrict__ idx_out)      // [B,F_out] or null (−1 on padding)
 {
+    pdl_prologue();
     __shared__ int s_cum[kLrMaxSmemT];
     __shared__ int s_idx[kLrTile];
     const int b = blockIdx.y;
@@ -120,7 +122,7 @@ extern "C" int fs2k_lr_scan(const int* durations, int B, int T, int* cum, int* t
     FS2K_REQUIRE(B >= 0 && T >= 0, FS2K_ERR_BAD_SHAPE);
     if (B == 0) return FS2K_OK;
     FS2K_REQUIRE(durations && cum && total, FS2K_ERR_NULL);
-    lr_scan_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(durations, B, T, cum, total);
+    fs2k_launch(lr_scan_kernel, dim3(cdiv(B, 4)), dim3(128), 0, (cudaStream_t)stream, durations, B, T, cum, total);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -136,9 +138,9 @@ extern "C" int fs2k_lr_gather(const float* x, const int* cum, const int* total, 
     FS2K_REQUIRE(!out_pos || inv_freq, FS2K_ERR_NULL);
     dim3 grid(cdiv(F_out, kLrTile), B);
     if (out_pos)
-        lr_gather_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, cum, total, T, D, F_out, out, out_pos, inv_freq, mask, idx_out);
+        fs2k_launch(lr_gather_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, cum, total, T, D, F_out, out, out_pos, inv_freq, mask, idx_out);
     else
-        lr_gather_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, cum, total, T, D, F_out, out, nullptr, nullptr, mask, idx_out);
+        fs2k_launch(lr_gather_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, cum, total, T, D, F_out, out, nullptr, nullptr, mask, idx_out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -21,6 +21,12 @@ extern "C" const char* fs2k_strerror(int code) {
     }
 }
 
+int g_fs2k_pdl_enabled = 1;
+extern "C" int fs2k_set_pdl(int enabled) {
+    g_fs2k_pdl_enabled = enabled ? 1 : 0;
+    return FS2K_OK;
+}
+
 extern "C" int fs2k_version(void) { return 100; }
 
 // 0 when the current device can run this sm_100a-only build
@@ -36,6 +42,7 @@ extern "C" int fs2k_check_device(void) {
 // Occupies the stream for `ns` nanoseconds (bench.py's roofline pass queues work behind it so that the
 // per-kernel CUDA-event timings that follow are not stretched by host launch gaps).
 __global__ void spin_kernel(unsigned long long ns) {
+    pdl_launch_dependents();
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
@@ -45,7 +52,7 @@ __global__ void spin_kernel(unsigned long long ns) {
 
 extern "C" int fs2k_spin_ns(long ns, fs2k_stream_t stream) {
     FS2K_REQUIRE(ns >= 0 && ns <= 2000000000L, FS2K_ERR_BAD_SHAPE);
-    spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)ns);
+    fs2k_launch(spin_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long)ns);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256)
 masked_loss_fwd_kernel(const float* __restrict__ pred, const void* __restrict__ target,
                        const uint8_t* __restrict__ row_mask, long M, int C, int kind /*0 mse, 1 mae*/,
                        double* __restrict__ sum) {
+    pdl_prologue();
     const long N = M * C;
     double acc = 0.0;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -34,6 +35,7 @@ masked_loss_fwd_kernel(const float* __restrict__ pred, const void* __restrict__ 
 
 // loss = sum · weight / N
 __global__ void scalar_finalize_kernel(const double* __restrict__ sum, double mul, float* __restrict__ out) {
+    pdl_prologue();
     out[0] = (float)(sum[0] * mul);
 }
 
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(256)
 masked_loss_bwd_kernel(const float* __restrict__ pred, const void* __restrict__ target,
                        const uint8_t* __restrict__ row_mask, long M, int C, int kind, float coef,
                        const float* __restrict__ gout, float* __restrict__ dpred) {
+    pdl_prologue();
     const long N = M * C;
     const float g = gout[0] * coef;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -59,6 +62,7 @@ masked_loss_bwd_kernel(const float* __restrict__ pred, const void* __restrict__ 
 __global__ void __launch_bounds__(256)
 bin_loss_fwd_kernel(const float* __restrict__ hard, const float* __restrict__ soft, long N, float eps,
                     double* __restrict__ sums) {
+    pdl_prologue();
     double a = 0.0, c = 0.0;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const float h = hard[i];
@@ -78,12 +82,14 @@ bin_loss_fwd_kernel(const float* __restrict__ hard, const float* __restrict__ so
     }
 }
 __global__ void bin_loss_finalize_kernel(const double* __restrict__ sums, float* __restrict__ out) {
+    pdl_prologue();
     out[0] = (float)(-sums[0] / sums[1]);
 }
 // dsoft = −g / Σhard · [hard==1 ∧ soft ≥ eps] / soft     (clamp passes no gradient below eps)
 __global__ void __launch_bounds__(256)
 bin_loss_bwd_kernel(const float* __restrict__ hard, const float* __restrict__ soft, long N, float eps,
                     const double* __restrict__ sums, const float* __restrict__ gout, float* __restrict__ dsoft) {
+    pdl_prologue();
     const float g = -gout[0] / (float)sums[1];
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const float s = soft[i];
@@ -95,6 +101,7 @@ bin_loss_bwd_kernel(const float* __restrict__ hard, const float* __restrict__ so
 __global__ void __launch_bounds__(256)
 axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta, long N,
              float* __restrict__ out) {
+    pdl_prologue();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
         out[i] = a[i] * alpha + (b ? b[i] * beta : 0.f);
 }
@@ -103,12 +110,14 @@ axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ ids, long R, int D,
                    float* __restrict__ out) {
+    pdl_prologue();
     const long N = R * D;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
         out[i] = table[(size_t)ids[i / D] * D + (i % D)];
 }
 
 __global__ void tanh_kernel(const float* __restrict__ x, long N, float* __restrict__ y) {
+    pdl_prologue();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) y[i] = tanhf(x[i]);
 }
@@ -133,11 +142,11 @@ extern "C" int fs2k_masked_loss_fwd(const float* pred, const void* target, int t
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     const long N = M * C;
     if (N > 0) {
-        if (target_is_int_log1p) masked_loss_fwd_kernel<true><<<ew_grid(N), 256, 0, s>>>(pred, target, row_mask, M, C, kind, scratch);
-        else masked_loss_fwd_kernel<false><<<ew_grid(N), 256, 0, s>>>(pred, target, row_mask, M, C, kind, scratch);
+        if (target_is_int_log1p) fs2k_launch(masked_loss_fwd_kernel<true>, dim3(ew_grid(N)), dim3(256), 0, s, pred, target, row_mask, M, C, kind, scratch);
+        else fs2k_launch(masked_loss_fwd_kernel<false>, dim3(ew_grid(N)), dim3(256), 0, s, pred, target, row_mask, M, C, kind, scratch);
         FS2K_CHECK_LAUNCH();
     }
-    scalar_finalize_kernel<<<1, 1, 0, s>>>(scratch, N > 0 ? (double)weight / (double)N : 0.0, loss);
+    fs2k_launch(scalar_finalize_kernel, dim3(1), dim3(1), 0, s, scratch, N > 0 ? (double)weight / (double)N : 0.0, loss);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -151,8 +160,8 @@ extern "C" int fs2k_masked_loss_bwd(const float* pred, const void* target, int t
     FS2K_REQUIRE(pred && target && row_mask && gout && dpred, FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
     const float coef = weight / (float)N;
-    if (target_is_int_log1p) masked_loss_bwd_kernel<true><<<ew_grid(N), 256, 0, s>>>(pred, target, row_mask, M, C, kind, coef, gout, dpred);
-    else masked_loss_bwd_kernel<false><<<ew_grid(N), 256, 0, s>>>(pred, target, row_mask, M, C, kind, coef, gout, dpred);
+    if (target_is_int_log1p) fs2k_launch(masked_loss_bwd_kernel<true>, dim3(ew_grid(N)), dim3(256), 0, s, pred, target, row_mask, M, C, kind, coef, gout, dpred);
+    else fs2k_launch(masked_loss_bwd_kernel<false>, dim3(ew_grid(N)), dim3(256), 0, s, pred, target, row_mask, M, C, kind, coef, gout, dpred);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -165,10 +174,10 @@ extern "C" int fs2k_bin_loss_fwd(const float* hard, const float* soft, long N, f
     cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), s);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (N > 0) {
-        bin_loss_fwd_kernel<<<ew_grid(N), 256, 0, s>>>(hard, soft, N, eps, sums);
+        fs2k_launch(bin_loss_fwd_kernel, dim3(ew_grid(N)), dim3(256), 0, s, hard, soft, N, eps, sums);
         FS2K_CHECK_LAUNCH();
     }
-    bin_loss_finalize_kernel<<<1, 1, 0, s>>>(sums, loss);
+    fs2k_launch(bin_loss_finalize_kernel, dim3(1), dim3(1), 0, s, sums, loss);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -178,7 +187,7 @@ extern "C" int fs2k_bin_loss_bwd(const float* hard, const float* soft, long N, f
     FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(hard && soft && sums && gout && dsoft, FS2K_ERR_NULL);
-    bin_loss_bwd_kernel<<<ew_grid(N), 256, 0, (cudaStream_t)stream>>>(hard, soft, N, eps, sums, gout, dsoft);
+    fs2k_launch(bin_loss_bwd_kernel, dim3(ew_grid(N)), dim3(256), 0, (cudaStream_t)stream, hard, soft, N, eps, sums, gout, dsoft);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -188,7 +197,7 @@ extern "C" int fs2k_axpby(const float* a, float alpha, const float* b, float bet
     FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(a && out, FS2K_ERR_NULL);
-    axpby_kernel<<<ew_grid(N), 256, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, N, out);
+    fs2k_launch(axpby_kernel, dim3(ew_grid(N)), dim3(256), 0, (cudaStream_t)stream, a, alpha, b, beta, N, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -198,7 +207,7 @@ extern "C" int fs2k_gather_rows(const float* table, const long long* ids, long R
     FS2K_REQUIRE(R >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     if (R == 0) return FS2K_OK;
     FS2K_REQUIRE(table && ids && out, FS2K_ERR_NULL);
-    gather_rows_kernel<<<ew_grid(R * D), 256, 0, (cudaStream_t)stream>>>(table, ids, R, D, out);
+    fs2k_launch(gather_rows_kernel, dim3(ew_grid(R * D)), dim3(256), 0, (cudaStream_t)stream, table, ids, R, D, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -207,7 +216,7 @@ extern "C" int fs2k_tanh(const float* x, long N, float* y, fs2k_stream_t stream)
     FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(x && y, FS2K_ERR_NULL);
-    tanh_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(x, N, y);
+    fs2k_launch(tanh_kernel, dim3(cdiv(N, 256)), dim3(256), 0, (cudaStream_t)stream, x, N, y);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

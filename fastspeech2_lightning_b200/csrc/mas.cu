@@ -45,6 +45,7 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
               int* __restrict__ path,            // [B,F] column of frame f, −1 on padding
               int* __restrict__ durations)       // [B,T]
 {
+    pdl_prologue();
     extern __shared__ float ring[];  // [PF][CHUNKS·blockDim] then uint32 sdir[MAS_DB][W]
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
@@ -165,6 +166,7 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
 // HBM-bound pass, so the sequential DP loop carries no transcendental
 __global__ void __launch_bounds__(256)
 mas_log_kernel(const float* __restrict__ x, long N, float* __restrict__ y) {
+    pdl_prologue();
     const long N4 = N >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (long)gridDim.x * blockDim.x) {
         const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
@@ -177,6 +179,7 @@ mas_log_kernel(const float* __restrict__ x, long N, float* __restrict__ y) {
 // dense 0/1 map [B,1,F,T] from the per-frame column index: HBM-write bound (4·B·F·T bytes)
 __global__ void __launch_bounds__(256)
 mas_dense_kernel(const int* __restrict__ path, int B, int F, int T, float* __restrict__ hard) {
+    pdl_prologue();
     const long rows = (long)B * F;
     const int lane = threadIdx.x & 31;
     for (long row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
@@ -202,7 +205,7 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
         cudaError_t e = cudaFuncSetAttribute(mas_dp_kernel<CHUNKS, PF, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    mas_dp_kernel<CHUNKS, PF, LOG><<<B, threads, smem, s>>>(attn, in_lens, out_lens, F, T, W, dirs, path, durations);
+    fs2k_launch(mas_dp_kernel<CHUNKS, PF, LOG>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
     return cudaGetLastError();
 }
 
@@ -237,7 +240,7 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
         long g = (n / 4 + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
         if (g < 1) g = 1;
-        mas_log_kernel<<<(int)g, 256, 0, s>>>(attn, n, logbuf);
+        fs2k_launch(mas_log_kernel, dim3((int)g), dim3(256), 0, s, attn, n, logbuf);
         FS2K_CHECK_LAUNCH();
         attn = logbuf;
     }
@@ -252,7 +255,7 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
         const long rows = (long)B * F;
         int grid = (int)((rows + 7) / 8);
         if (grid > 148 * 16) grid = 148 * 16;
-        mas_dense_kernel<<<grid, 256, 0, s>>>(path, B, F, T, hard);
+        fs2k_launch(mas_dense_kernel, dim3(grid), dim3(256), 0, s, path, B, F, T, hard);
         FS2K_CHECK_LAUNCH();
     }
     return FS2K_OK;

@@ -11,6 +11,7 @@ template <int K, bool GLU>
 __global__ void __launch_bounds__(256)
 dwconv_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ x, int ldx, int L, int C,
                   const float* __restrict__ w, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dbias) {
+    pdl_prologue();
     constexpr int P = (K - 1) / 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.z;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256)
 rowdot_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                   const uint8_t* __restrict__ mask, long M, int D, float* __restrict__ dx, float* __restrict__ dw,
                   float* __restrict__ db) {
+    pdl_prologue();
     __shared__ float s_red[8][1024];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D4 = D >> 2;
@@ -104,6 +106,7 @@ rowdot_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, cons
 __global__ void __launch_bounds__(256)
 lr_bwd_kernel(const float* __restrict__ g1, const float* __restrict__ g2, const int* __restrict__ cum, int B, int T,
               int D, int F, float* __restrict__ dx) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int D4 = D >> 2;
     const long n = (long)B * T;
@@ -126,6 +129,7 @@ template <typename IdT>
 __global__ void __launch_bounds__(256)
 scatter_add_rows_kernel(const float* __restrict__ g1, const float* __restrict__ g2, const IdT* __restrict__ ids, long N,
                         int D, long skip_id, float* __restrict__ dtable) {
+    pdl_prologue();
     const long total = N * D;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long n = i / D;
@@ -141,6 +145,7 @@ scatter_add_rows_kernel(const float* __restrict__ g1, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 rows_sum_scatter_kernel(const float* __restrict__ g, const int* __restrict__ ids, int B, int L, int D,
                         float* __restrict__ drows) {
+    pdl_prologue();
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= D) return;
@@ -155,6 +160,7 @@ aligner_bwd_rows_kernel(const float* __restrict__ g_soft, const float* __restric
                         const float* __restrict__ soft, const float* __restrict__ logprob,
                         const float* __restrict__ prior, const int* __restrict__ key_lens, int B, int F, int T,
                         float* __restrict__ dd) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long n_rows = (long)B * F;
     for (long row = (long)blockIdx.x * 4 + warp; row < n_rows; row += (long)gridDim.x * 4) {
@@ -189,6 +195,7 @@ template <bool TRANS>
 __global__ void __launch_bounds__(256)
 aligner_bwd_proj_kernel(const float* __restrict__ Wm, const float* __restrict__ V, const float* __restrict__ U, int I,
                         int J, int C, float coef, float* __restrict__ out) {
+    pdl_prologue();
     __shared__ float Ws[64][65];
     __shared__ float Vs[64][81];
     const int b = blockIdx.y, i0 = blockIdx.x * 64;
@@ -260,8 +267,8 @@ static int launch_dwb(const float* gz, const float* x, int ldx, int B, int L, in
                       float* dw, float* dbias, cudaStream_t s) {
     const int threads = C < 256 ? ((C + 31) / 32) * 32 : 256;
     dim3 grid(cdiv(C, threads), cdiv(L, kDwbTile), B);
-    if (glu) dwconv_bwd_kernel<K, true><<<grid, threads, 0, s>>>(gz, x, ldx, L, C, w, dx, dw, dbias);
-    else dwconv_bwd_kernel<K, false><<<grid, threads, 0, s>>>(gz, x, ldx, L, C, w, dx, dw, dbias);
+    if (glu) fs2k_launch(dwconv_bwd_kernel<K, true>, dim3(grid), dim3(threads), 0, s, gz, x, ldx, L, C, w, dx, dw, dbias);
+    else fs2k_launch(dwconv_bwd_kernel<K, false>, dim3(grid), dim3(threads), 0, s, gz, x, ldx, L, C, w, dx, dw, dbias);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -299,7 +306,7 @@ extern "C" int fs2k_rowdot_bwd(const float* g, const float* x, const float* w, c
     if (M == 0) return FS2K_OK;
     long grid = (M + 63) / 64;
     if (grid > 148 * 2) grid = 148 * 2;
-    rowdot_bwd_kernel<<<(int)grid, 256, 0, s>>>(g, x, w, mask, M, D, dx, dw, db);
+    fs2k_launch(rowdot_bwd_kernel, dim3((int)grid), dim3(256), 0, s, g, x, w, mask, M, D, dx, dw, db);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -310,7 +317,7 @@ extern "C" int fs2k_lr_bwd(const float* g_out, const float* g_out_pos, const int
     FS2K_REQUIRE((D & 3) == 0, FS2K_ERR_UNSUPPORTED);
     if ((long)B * T == 0) return FS2K_OK;
     FS2K_REQUIRE(cum && dx, FS2K_ERR_NULL);
-    lr_bwd_kernel<<<ew_grid3((long)B * T, 8), 256, 0, (cudaStream_t)stream>>>(g_out, g_out_pos, cum, B, T, D, F, dx);
+    fs2k_launch(lr_bwd_kernel, dim3(ew_grid3((long)B * T, 8)), dim3(256), 0, (cudaStream_t)stream, g_out, g_out_pos, cum, B, T, D, F, dx);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -321,8 +328,8 @@ extern "C" int fs2k_scatter_add_rows(const float* g1, const float* g2, const voi
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(g1 && ids && dtable, FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
-    if (ids_are_int64) scatter_add_rows_kernel<long long><<<ew_grid3(N * D), 256, 0, s>>>(g1, g2, (const long long*)ids, N, D, skip_id, dtable);
-    else scatter_add_rows_kernel<int><<<ew_grid3(N * D), 256, 0, s>>>(g1, g2, (const int*)ids, N, D, skip_id, dtable);
+    if (ids_are_int64) fs2k_launch(scatter_add_rows_kernel<long long>, dim3(ew_grid3(N * D)), dim3(256), 0, s, g1, g2, (const long long*)ids, N, D, skip_id, dtable);
+    else fs2k_launch(scatter_add_rows_kernel<int>, dim3(ew_grid3(N * D)), dim3(256), 0, s, g1, g2, (const int*)ids, N, D, skip_id, dtable);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -333,7 +340,7 @@ extern "C" int fs2k_rows_sum_scatter(const float* g, const int* ids, int B, int 
     if (B == 0) return FS2K_OK;
     FS2K_REQUIRE(g && drows, FS2K_ERR_NULL);
     FS2K_REQUIRE(B <= 65535, FS2K_ERR_UNSUPPORTED);
-    rows_sum_scatter_kernel<<<dim3(cdiv(D, 128), B), 128, 0, (cudaStream_t)stream>>>(g, ids, B, L, D, drows);
+    fs2k_launch(rows_sum_scatter_kernel, dim3(dim3(cdiv(D, 128), B)), dim3(128), 0, (cudaStream_t)stream, g, ids, B, L, D, drows);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -350,11 +357,11 @@ extern "C" int fs2k_aligner_bwd(const float* g_soft, const float* g_logprob, con
     cudaStream_t s = (cudaStream_t)stream;
     long g = ((long)B * F + 3) / 4;
     if (g > 148 * 16) g = 148 * 16;
-    aligner_bwd_rows_kernel<<<(int)g, 128, 0, s>>>(g_soft, g_logprob, soft, logprob, prior, key_lens, B, F, T, dd);
+    fs2k_launch(aligner_bwd_rows_kernel, dim3((int)g), dim3(128), 0, s, g_soft, g_logprob, soft, logprob, prior, key_lens, B, F, T, dd);
     FS2K_CHECK_LAUNCH();
-    aligner_bwd_proj_kernel<false><<<dim3(cdiv(F, 64), B), 256, 0, s>>>(dd, k, q, F, T, C, 0.001f, dq);
+    fs2k_launch(aligner_bwd_proj_kernel<false>, dim3(dim3(cdiv(F, 64), B)), dim3(256), 0, s, dd, k, q, F, T, C, 0.001f, dq);
     FS2K_CHECK_LAUNCH();
-    aligner_bwd_proj_kernel<true><<<dim3(cdiv(T, 64), B), 256, 0, s>>>(dd, q, k, T, F, C, 0.001f, dk);
+    fs2k_launch(aligner_bwd_proj_kernel<true>, dim3(dim3(cdiv(T, 64), B)), dim3(256), 0, s, dd, q, k, T, F, C, 0.001f, dk);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

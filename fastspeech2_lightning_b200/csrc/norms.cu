@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, long M, int D, float drop_p, unsigned long long seed, float* __restrict__ y,
                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int lane = threadIdx.x & 31;
@@ -74,6 +75,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // CTA = 256 threads = 8 row-groups × 32 channel lanes (float4 → 128 channels per pass).
 __global__ void __launch_bounds__(256)
 colstats_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, double* __restrict__ sums) {
+    pdl_prologue();
     __shared__ double s_part[8][128][2];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta;
@@ -122,6 +124,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long M, int 
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_rstd) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   int act, const float* __restrict__ residual, long M, int C, float drop_p, unsigned long long seed,
                   float* __restrict__ y) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
@@ -194,9 +198,9 @@ extern "C" int fs2k_layernorm_fwd(const float* x, const float* gamma, const floa
     long g = (M + 7) / 8;
     if (g > 148 * 8) g = 148 * 8;
     cudaStream_t s = (cudaStream_t)stream;
-    if (D <= 256) layernorm_kernel<2><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
-    else if (D <= 512) layernorm_kernel<4><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
-    else layernorm_kernel<8><<<(int)g, 256, 0, s>>>(x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
+    if (D <= 256) fs2k_launch(layernorm_kernel<2>, dim3((int)g), dim3(256), 0, s, x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
+    else if (D <= 512) fs2k_launch(layernorm_kernel<4>, dim3((int)g), dim3(256), 0, s, x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
+    else fs2k_launch(layernorm_kernel<8>, dim3((int)g), dim3(256), 0, s, x, gamma, beta, eps, M, D, dropout_p, useed, y, mean_out, rstd_out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -212,7 +216,7 @@ extern "C" int fs2k_colstats(const float* z, long M, int C, double* sums /* [2*C
     if (M == 0) return FS2K_OK;
     long rows_per_cta;
     const dim3 grid = col_reduce_grid(M, C, &rows_per_cta);
-    colstats_kernel<<<grid, 256, 0, s>>>(z, M, C, rows_per_cta, sums);
+    fs2k_launch(colstats_kernel, dim3(grid), dim3(256), 0, s, z, M, C, rows_per_cta, sums);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -224,7 +228,7 @@ extern "C" int fs2k_bn_finalize(const double* sums, long M, int C, const float* 
     FS2K_REQUIRE(C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(scale && shift, FS2K_ERR_NULL);
     FS2K_REQUIRE(training ? (sums != nullptr) : (running_mean && running_var), FS2K_ERR_NULL);
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum, training,
+    fs2k_launch(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, M, C, gamma, beta, eps, momentum, training,
                                                                        running_mean, running_var, num_batches_tracked,
                                                                        scale, shift, save_mean, save_rstd);
     FS2K_CHECK_LAUNCH();
@@ -239,7 +243,7 @@ extern "C" int fs2k_affine_act(const float* z, const float* scale, const float* 
     FS2K_REQUIRE(z && y && (!scale || shift), FS2K_ERR_NULL);  // scale == NULL: plain activation
     long g = (M * (C >> 2) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    affine_act_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(z, scale, shift, act, residual, M, C, dropout_p,
+    fs2k_launch(affine_act_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, z, scale, shift, act, residual, M, C, dropout_p,
                                                                 (unsigned long long)seed, y);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -10,6 +10,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                      const float* __restrict__ rstd, const float* __restrict__ gamma, long M, int D, float drop_p,
                      unsigned long long seed, float* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ float s_red[8][32 * MAXV * 4];
@@ -102,6 +103,7 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                     int act, long M, int C, long rows_per_cta, float drop_p, unsigned long long seed,
                     double* __restrict__ sums) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     __shared__ double s_part[8][128][2];
@@ -160,6 +162,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     const double* __restrict__ sums, int act, int training, long M, int C, float drop_p,
                     unsigned long long seed, float* __restrict__ gz, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
+    pdl_prologue();
     seed = seed_with_base(seed);
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
     const int C4 = C >> 2;
@@ -212,9 +215,9 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
     long grid = (M + 63) / 64;  // ≥ 8 rows per warp so the per-CTA atomics amortise
     if (grid > 148 * 4) grid = 148 * 4;
     if (grid < 1) grid = 1;
-    if (D <= 256) layernorm_bwd_kernel<2><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
-    else if (D <= 512) layernorm_bwd_kernel<4><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
-    else layernorm_bwd_kernel<8><<<(int)grid, 256, 0, s>>>(g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    if (D <= 256) fs2k_launch(layernorm_bwd_kernel<2>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    else if (D <= 512) fs2k_launch(layernorm_bwd_kernel<4>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    else fs2k_launch(layernorm_bwd_kernel<8>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -233,11 +236,11 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     if (M == 0) return FS2K_OK;
     long rows;
     const dim3 sgrid = col_reduce_grid(M, C, &rows);
-    bn_bwd_stats_kernel<<<sgrid, 256, 0, s>>>(g, z, scale, shift, mean, rstd, act, M, C, rows, dropout_p, useed, sums);
+    fs2k_launch(bn_bwd_stats_kernel, dim3(sgrid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, act, M, C, rows, dropout_p, useed, sums);
     FS2K_CHECK_LAUNCH();
     long grid = (M * (C >> 2) + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    bn_bwd_apply_kernel<<<(int)grid, 256, 0, s>>>(g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, gz, dgamma, dbeta);
+    fs2k_launch(bn_bwd_apply_kernel, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, gz, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

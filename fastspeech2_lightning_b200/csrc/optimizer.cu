@@ -7,6 +7,7 @@ namespace fs2k {
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, long N, double* __restrict__ out) {
+    pdl_prologue();
     double acc = 0.0;
     const long N4 = N >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (long)gridDim.x * blockDim.x) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long N,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
              float grad_scale, const double* __restrict__ sumsq, const float* __restrict__ step_state) {
+    pdl_prologue();
     if (step_state) {  // graph replay: the step's scalars come from device memory
         lr = step_state[0];
         bc1 = step_state[1];
@@ -68,7 +70,7 @@ extern "C" int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t str
     long grid = (N / 4 + 255) / 256;
     if (grid > 148 * 4) grid = 148 * 4;
     if (grid < 1) grid = 1;
-    sumsq_kernel<<<(int)grid, 256, 0, s>>>(g, N, out);
+    fs2k_launch(sumsq_kernel, dim3((int)grid), dim3(256), 0, s, g, N, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -83,7 +85,7 @@ extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, lon
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    adamw_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,
+    fs2k_launch(adamw_kernel, dim3((int)grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,
                                                              bc2_sqrt, max_norm, grad_scale, sumsq, nullptr);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
@@ -97,7 +99,7 @@ extern "C" int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v,
     FS2K_REQUIRE(p && g && m && v && step_state, FS2K_ERR_NULL);
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    adamw_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, N, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
+    fs2k_launch(adamw_kernel, dim3((int)grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, N, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
                                                              max_norm, grad_scale, sumsq, step_state);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
@@ -106,6 +108,7 @@ extern "C" int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v,
 namespace fs2k {
 __global__ void set_step_state_kernel(float* __restrict__ st, unsigned long long* __restrict__ seed_base, float lr, float bc1,
                                       float bc2_sqrt, unsigned long long base) {
+    pdl_prologue();
     if (st) { st[0] = lr; st[1] = bc1; st[2] = bc2_sqrt; st[3] = 0.f; }
     if (seed_base) seed_base[0] = base;
 }
@@ -114,7 +117,7 @@ __global__ void set_step_state_kernel(float* __restrict__ st, unsigned long long
 extern "C" int fs2k_set_step_state(float* step_state, unsigned long long* seed_base, float lr, float bias_correction1,
                                    float bias_correction2_sqrt, long seed_base_value, fs2k_stream_t stream) {
     FS2K_REQUIRE(step_state || seed_base, FS2K_ERR_NULL);
-    set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_state, seed_base, lr, bias_correction1, bias_correction2_sqrt,
+    fs2k_launch(set_step_state_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_state, seed_base, lr, bias_correction1, bias_correction2_sqrt,
                                                             (unsigned long long)seed_base_value);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -29,6 +29,7 @@ bucketize_embed_add_kernel(const float* __restrict__ v_in,   // [N] value to buc
                            float* __restrict__ y,            // [N,D] = x + table[id]   (may alias x)
                            long long* __restrict__ ids,      // [N] int64 or null
                            long N, int D) {
+    pdl_prologue();
     extern __shared__ float s_bins[];
     for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_bins[i] = bins[i];
     __syncthreads();
@@ -56,6 +57,7 @@ bucketize_embed_add_kernel(const float* __restrict__ v_in,   // [N] value to buc
 
 __global__ void bucketize_kernel(const float* __restrict__ v, const float* __restrict__ bins, int n_bins,
                                  long long* __restrict__ ids, long N) {
+    pdl_prologue();
     long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) ids[n] = bucket_of(v[n], bins, n_bins);
 }
@@ -67,6 +69,7 @@ __global__ void bucketize_kernel(const float* __restrict__ v, const float* __res
 __global__ void average_variance_kernel(const float* __restrict__ var,  // [B,F]
                                         const int* __restrict__ cum,    // [B,T] inclusive cumsum of durations
                                         int B, int F, int T, float* __restrict__ out) {
+    pdl_prologue();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)B * T) return;
     const int b = (int)(i / T), t = (int)(i % T);
@@ -85,6 +88,7 @@ __global__ void average_variance_kernel(const float* __restrict__ var,  // [B,F]
 // dur = int(clamp(rint(exp(logd) − 1) · control, min 0))   (round half to even, truncating cast)
 __global__ void round_durations_kernel(const float* __restrict__ log_dur, const uint8_t* __restrict__ mask,
                                        float control, long N, int* __restrict__ dur) {
+    pdl_prologue();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float d = rintf(__fadd_rn(expf(log_dur[i]), -1.0f));
@@ -101,6 +105,7 @@ __global__ void __launch_bounds__(256)
 embed_posenc_kernel(const int* __restrict__ text, const float* __restrict__ table, int n_sym,
                     const float* __restrict__ inv_freq, const int* __restrict__ lens, int B, int T, int D,
                     float* __restrict__ emb, float* __restrict__ x, int* __restrict__ err) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int D4 = D >> 2, half = D >> 1;
     const long N = (long)B * T;
@@ -136,6 +141,7 @@ embed_posenc_kernel(const int* __restrict__ text, const float* __restrict__ tabl
 __global__ void __launch_bounds__(256)
 add_posenc_kernel(const float* __restrict__ x_in, const float* __restrict__ inv_freq, const int* __restrict__ lens,
                   int B, int L, int D, float* __restrict__ x) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int half = D >> 1;
     const long N = (long)B * L;
@@ -158,6 +164,7 @@ add_posenc_kernel(const float* __restrict__ x_in, const float* __restrict__ inv_
 __global__ void __launch_bounds__(256)
 add_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int L, int D,
                 const float* r0, const int* i0, const float* r1, const int* i1, const float* r2, const int* i2) {
+    pdl_prologue();
     const long N = (long)B * L * (D >> 2);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const int q = (int)(i % (D >> 2));
@@ -178,6 +185,7 @@ add_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int L
 
 // lens[b] = #{mask[b,:] != 0} ; one warp per utterance (fs2/model.py:226-230)
 __global__ void mask_lens_kernel(const uint8_t* __restrict__ mask, int B, int L, int* __restrict__ lens) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -205,8 +213,7 @@ extern "C" int fs2k_bucketize_embed_add(const float* v, float scale, float* v_sc
     FS2K_REQUIRE((D & 3) == 0 && n_bins <= 8192, FS2K_ERR_UNSUPPORTED);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(v && bins && table && x && y, FS2K_ERR_NULL);
-    bucketize_embed_add_kernel<<<grid_for_warps(N, 8), 256, n_bins * sizeof(float), (cudaStream_t)stream>>>(
-        v, scale, v_scaled, bins, n_bins, table, x, y, ids, N, D);
+    fs2k_launch(bucketize_embed_add_kernel, dim3(grid_for_warps(N, 8)), dim3(256), n_bins * sizeof(float), (cudaStream_t)stream, v, scale, v_scaled, bins, n_bins, table, x, y, ids, N, D);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -216,7 +223,7 @@ extern "C" int fs2k_bucketize(const float* v, const float* bins, int n_bins, lon
     FS2K_REQUIRE(N >= 0 && n_bins >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(v && bins && ids, FS2K_ERR_NULL);
-    bucketize_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(v, bins, n_bins, ids, N);
+    fs2k_launch(bucketize_kernel, dim3(cdiv(N, 256)), dim3(256), 0, (cudaStream_t)stream, v, bins, n_bins, ids, N);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -226,7 +233,7 @@ extern "C" int fs2k_average_variance(const float* var, const int* cum, int B, in
     FS2K_REQUIRE(B >= 0 && F >= 0 && T >= 0, FS2K_ERR_BAD_SHAPE);
     if ((long)B * T == 0) return FS2K_OK;
     FS2K_REQUIRE(var && cum && out, FS2K_ERR_NULL);
-    average_variance_kernel<<<cdiv((long)B * T, 128), 128, 0, (cudaStream_t)stream>>>(var, cum, B, F, T, out);
+    fs2k_launch(average_variance_kernel, dim3(cdiv((long)B * T, 128)), dim3(128), 0, (cudaStream_t)stream, var, cum, B, F, T, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -235,7 +242,7 @@ extern "C" int fs2k_round_durations(const float* log_dur, float control, long N,
     FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(log_dur && dur, FS2K_ERR_NULL);
-    round_durations_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(log_dur, nullptr, control, N, dur);
+    fs2k_launch(round_durations_kernel, dim3(cdiv(N, 256)), dim3(256), 0, (cudaStream_t)stream, log_dur, nullptr, control, N, dur);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -247,8 +254,7 @@ extern "C" int fs2k_embed_posenc(const int* text, const float* table, int n_sym,
     FS2K_REQUIRE((D & 3) == 0, FS2K_ERR_UNSUPPORTED);
     if ((long)B * T == 0) return FS2K_OK;
     FS2K_REQUIRE(text && table && inv_freq && lens && x, FS2K_ERR_NULL);
-    embed_posenc_kernel<<<grid_for_warps((long)B * T, 8), 256, 0, (cudaStream_t)stream>>>(
-        text, table, n_sym, inv_freq, lens, B, T, D, emb, x, err_flag);
+    fs2k_launch(embed_posenc_kernel, dim3(grid_for_warps((long)B * T, 8)), dim3(256), 0, (cudaStream_t)stream, text, table, n_sym, inv_freq, lens, B, T, D, emb, x, err_flag);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -258,7 +264,7 @@ extern "C" int fs2k_add_posenc(const float* x_in, const float* inv_freq, const i
     FS2K_REQUIRE(B >= 0 && L >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     if ((long)B * L == 0) return FS2K_OK;
     FS2K_REQUIRE(x_in && inv_freq && lens && x, FS2K_ERR_NULL);
-    add_posenc_kernel<<<grid_for_warps((long)B * L, 8), 256, 0, (cudaStream_t)stream>>>(x_in, inv_freq, lens, B, L, D, x);
+    fs2k_launch(add_posenc_kernel, dim3(grid_for_warps((long)B * L, 8)), dim3(256), 0, (cudaStream_t)stream, x_in, inv_freq, lens, B, L, D, x);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -273,7 +279,7 @@ extern "C" int fs2k_add_rows(const float* x, float* y, int B, int L, int D, cons
     FS2K_REQUIRE(x && y, FS2K_ERR_NULL);
     long g = (N + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    add_rows_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, y, B, L, D, rows0, ids0, rows1, ids1, rows2, ids2);
+    fs2k_launch(add_rows_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, x, y, B, L, D, rows0, ids0, rows1, ids1, rows2, ids2);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -282,7 +288,7 @@ extern "C" int fs2k_mask_lens(const uint8_t* mask, int B, int L, int* lens, fs2k
     FS2K_REQUIRE(B >= 0 && L >= 0, FS2K_ERR_BAD_SHAPE);
     if (B == 0) return FS2K_OK;
     FS2K_REQUIRE(mask && lens, FS2K_ERR_NULL);
-    mask_lens_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(mask, B, L, lens);
+    fs2k_launch(mask_lens_kernel, dim3(cdiv(B, 4)), dim3(128), 0, (cudaStream_t)stream, mask, B, L, lens);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
@@ -290,6 +296,7 @@ extern "C" int fs2k_mask_lens(const uint8_t* mask, int B, int L, int* lens, fs2k
 namespace fs2k {
 // mask[b,l] = l < lens[b]   (fs2/utils/heavy.py:11-15)
 __global__ void lens_mask_kernel(const int* __restrict__ lens, int B, int L, uint8_t* __restrict__ mask) {
+    pdl_prologue();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (long)B * L) mask[i] = (int)(i % L) < lens[i / L];
 }
@@ -299,7 +306,7 @@ extern "C" int fs2k_lens_mask(const int* lens, int B, int L, uint8_t* mask, fs2k
     FS2K_REQUIRE(B >= 0 && L >= 0, FS2K_ERR_BAD_SHAPE);
     if ((long)B * L == 0) return FS2K_OK;
     FS2K_REQUIRE(lens && mask, FS2K_ERR_NULL);
-    fs2k::lens_mask_kernel<<<cdiv((long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(lens, B, L, mask);
+    fs2k_launch(fs2k::lens_mask_kernel, dim3(cdiv((long)B * L, 256)), dim3(256), 0, (cudaStream_t)stream, lens, B, L, mask);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

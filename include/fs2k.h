@@ -40,6 +40,9 @@ enum { FS2K_ACT_NONE = 0, FS2K_ACT_RELU = 1, FS2K_ACT_SILU = 2, FS2K_ACT_TANH = 
 const char* fs2k_strerror(int code);
 int fs2k_version(void);
 int fs2k_check_device(void); /* FS2K_OK iff the current device is compute capability 10.x */
+/* Programmatic dependent launch for every kernel of the library (default on): the next kernel of a stream / graph is
+ * scheduled while the previous one drains and waits in griddepcontrol.wait before touching memory.  0 = plain launches. */
+int fs2k_set_pdl(int enabled);
 /* keeps `stream` busy for ns nanoseconds (measurement aid: lets the host queue work ahead of the GPU) */
 int fs2k_spin_ns(long ns, fs2k_stream_t stream);
 
