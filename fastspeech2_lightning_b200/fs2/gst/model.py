@@ -4,8 +4,10 @@
 * `condition_on_gst_tokens` (reference-free synthesis, gst/model.py:77-85): a single key ⇒ the
   softmax is identically 1 ⇒ linear_out(linear_v(tanh(gst_embs[index]))), two libfs2k GEMMs.
 * `forward(speech)` (reference encoder: 6×Conv2d s2 + BatchNorm2d + ReLU → GRU → 4-head token
-  attention) is SURVEY §8(f) rank 3 — "next", not yet re-kerneled: it currently runs as cuDNN /
-  ATen library calls on the GPU (no CPU path), marked LIBRARY in DESIGN.md.
+  attention): synthesis / validation (eval mode, no gradient) runs on libfs2k
+  kernels (csrc/gst.cu: direct channels-last conv + folded BN + ReLU, GRU = tensor-core GEMMs + gate
+  kernel, token attention); training through it still uses torch autograd over cuDNN / ATen library
+  calls on the GPU (no CPU path), marked LIBRARY in DESIGN.md.
 """
 import math
 from collections.abc import Sequence
@@ -13,6 +15,13 @@ from collections.abc import Sequence
 import torch
 
 from ... import autograd as ag
+from ... import ops
+
+
+def _kernel_path(module, *tensors) -> bool:
+    """Kernels serve the no-gradient eval case; anything that needs autograd or batch statistics takes the library path."""
+    return (not module.training) and not (torch.is_grad_enabled() and (
+        any(t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters())))
 
 
 class MultiHeadedAttention(torch.nn.Module):
@@ -64,7 +73,19 @@ class ReferenceEncoder(torch.nn.Module):
         self.gru = torch.nn.GRU(gru_in_units, gru_units, gru_layers, batch_first=True)
 
     def forward(self, speech: torch.Tensor) -> torch.Tensor:
-        """LIBRARY path: gst/model.py:179-199."""
+        """gst/model.py:179-199.  Eval without gradients: libfs2k kernels; otherwise the LIBRARY path below."""
+        if _kernel_path(self, speech):
+            x = speech.detach().contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
+            n = len(self.convs) // 3
+            for i in range(n):
+                conv, bn = self.convs[3 * i], self.convs[3 * i + 1]
+                scale, shift = ops.bn_scale_shift(bn, None, False)
+                w = conv.weight.detach().permute(2, 3, 1, 0).contiguous()  # [Co,Ci,3,3] → [3,3,Ci,Co]
+                x = ops.conv2d_s2_bn_relu(x, w, scale, shift, cw_layout=(i == n - 1))
+            hs = x.reshape(x.shape[0], x.shape[1], -1)  # [B, T', C·W']
+            g = self.gru
+            return ops.gru_last_hidden(hs, g.weight_ih_l0.detach(), g.weight_hh_l0.detach(), g.bias_ih_l0.detach(),
+                                       g.bias_hh_l0.detach())
         batch_size = speech.size(0)
         hs = self.convs(speech.unsqueeze(1)).transpose(1, 2)
         hs = hs.contiguous().view(batch_size, hs.size(1), -1)
@@ -82,6 +103,14 @@ class StyleTokenLayer(torch.nn.Module):
                                         dropout_rate=dropout_rate)
 
     def forward(self, ref_embs: torch.Tensor) -> torch.Tensor:
+        if _kernel_path(self, ref_embs):
+            m = self.mha
+            tokens = ops.tanh(self.gst_embs.detach())
+            q = ops.gemm(ref_embs.detach().contiguous(), m.linear_q.weight.detach(), m.linear_q.bias.detach())
+            k = ops.gemm(tokens, m.linear_k.weight.detach(), m.linear_k.bias.detach())
+            v = ops.gemm(tokens, m.linear_v.weight.detach(), m.linear_v.bias.detach())
+            o = ops.gst_token_attention(q, k, v, m.h)
+            return ops.gemm(o, m.linear_out.weight.detach(), m.linear_out.bias.detach())
         batch_size = ref_embs.size(0)
         gst_embs = torch.tanh(self.gst_embs).unsqueeze(0).expand(batch_size, -1, -1)
         return self.mha(ref_embs.unsqueeze(1), gst_embs, gst_embs, None).squeeze(1)

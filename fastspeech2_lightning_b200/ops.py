@@ -526,6 +526,44 @@ def ctc_forward_sum_bwd(saved, gout, blank_logprob: float = -1.0):
     return dx
 
 
+def conv2d_s2_bn_relu(x, w_packed, scale, shift, cw_layout: bool = False):
+    """One GST ReferenceEncoder block on channels-last x [B,H,W,Ci]; w_packed [3,3,Ci,Co] → [B,Ho,Wo,Co] ([B,Ho,Co,Wo])."""
+    x = _f32(x, "x")
+    B, H, W, Ci = x.shape
+    Co = w_packed.shape[-1]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Co, Wo) if cw_layout else (B, Ho, Wo, Co), dtype=torch.float32, device=x.device)
+    check(lib().fs2k_conv2d_s2_bn_relu(_p(x), _p(_f32(w_packed, "w")), _p(scale), _p(shift), B, H, W, Ci, Co, int(cw_layout),
+                                       _p(y), _stream()), "fs2k_conv2d_s2_bn_relu")
+    _count()
+    return y
+
+
+def gru_last_hidden(x, w_ih, w_hh, b_ih, b_hh):
+    """Last hidden state [B,U] of a one-layer batch_first torch.nn.GRU over x [B,T,I], h0 = 0."""
+    x = _f32(x, "x")
+    B, T, I = x.shape
+    U = w_hh.shape[1]
+    xp = gemm(x.reshape(B * T, I), w_ih, b_ih)  # [B·T, 3U]: input projection of every step in one GEMM
+    h = torch.zeros((B, U), dtype=torch.float32, device=x.device)
+    for t in range(T):
+        hp = gemm(h, w_hh, b_hh)
+        h_new = torch.empty_like(h)
+        check(lib().fs2k_gru_gate(xp.data_ptr() + 4 * t * 3 * U, T * 3 * U, _p(hp), _p(h), B, U, _p(h_new), _stream()), "fs2k_gru_gate")
+        _count()
+        h = h_new
+    return h
+
+
+def gst_token_attention(q, k, v, heads: int):
+    q, k, v = _f32(q, "q"), _f32(k, "k"), _f32(v, "v")
+    B, D = q.shape
+    out = torch.empty_like(q)
+    check(lib().fs2k_gst_token_attention(_p(q), _p(k), _p(v), B, k.shape[0], heads, D // heads, _p(out), _stream()), "fs2k_gst_token_attention")
+    _count()
+    return out
+
+
 def axpby(a, alpha: float, b=None, beta: float = 0.0):
     a = _f32(a, "a")
     if b is not None:

@@ -242,6 +242,19 @@ int fs2k_aligner_bwd(const float* g_soft, const float* g_logprob, const float* s
                      const float* prior, const int* key_lens, const float* q, const float* k, int B, int F, int T,
                      int C, float* dd, float* dq, float* dk, fs2k_stream_t stream);
 
+/* ---- global style tokens, inference (fs2/gst/model.py:103-257) ------------------------------
+ * conv2d_s2_bn_relu: one ReferenceEncoder block — Conv2d(3x3, stride 2, pad 1, no bias) + folded BatchNorm2d + ReLU on
+ *   channels-last x [B,H,W,Ci]; w re-packed to [3][3][Ci][Co]; y [B,Ho,Wo,Co], or [B,Ho,Co,Wo] when cw_layout != 0
+ *   (the feature order `hs.transpose(1,2).view(B,T,C*W)` of :195-197 feeds the GRU with).
+ * gru_gate: torch.nn.GRU cell update from the two projections (both with their biases), gate order r,z,n (:198).
+ * gst_token_attention: multi-head attention of one query per batch row over T <= 32 tokens (gst/attn.py:172-194). */
+int fs2k_conv2d_s2_bn_relu(const float* x, const float* w_khwcico, const float* scale, const float* shift, int B, int H,
+                           int W, int Ci, int Co, int cw_layout, float* y, fs2k_stream_t stream);
+int fs2k_gru_gate(const float* xproj, long xproj_row_stride, const float* hproj, const float* h, int B, int U, float* h_out,
+                  fs2k_stream_t stream);
+int fs2k_gst_token_attention(const float* q, const float* k, const float* v, int B, int T, int heads, int dk, float* out,
+                             fs2k_stream_t stream);
+
 /* ---- optimizer over one flat buffer (torch.optim.AdamW at fs2/model.py:530-537; clip 1.0 at fs2/cli/train.py:38) ---
  * sumsq: out[0] = Σ g² (fp64).  adamw_step: g' = g·grad_scale·min(1, max_norm/(‖g·grad_scale‖+1e-6)) when sumsq is given
  * (grad_scale = 1/world_size folds the data-parallel mean), then AdamW with decoupled weight decay and bias correction

@@ -182,3 +182,36 @@ def test_c1_shape_against_oracle_on_cpu():
     close(got["output"], want["output"], FP32_TOL, "C1 output")
     close(got["postnet_output"], want["postnet_output"], FP32_TOL, "C1 postnet_output")
     close(got["duration_prediction"], want["duration_prediction"], FP32_TOL, "C1 log-dur")
+
+
+@pytest.mark.parametrize("B,F", [(3, 97), (8, 500), (1, 64)])
+def test_gst_style_encoder_kernels_match_the_oracle(B, F):
+    """Synthesis-time StyleEncoder (6 × Conv2d s2 + BN2d + ReLU → GRU → token attention) on libfs2k kernels against the
+    oracle's torch-CPU restatement of gst/model.py:87-257, with non-trivial BatchNorm running statistics."""
+    from fastspeech2_lightning_b200.fs2.gst.model import StyleEncoder
+    from oracle.fs2_oracle import gst_style_encoder
+
+    torch.manual_seed(B * 100 + F)
+    enc = StyleEncoder(idim=80)
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0.0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0.0, 0.2)
+    enc.eval()
+    speech = torch.randn(B, F, 80)
+    sd = {"gst." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    ref = gst_style_encoder(speech, sd, training=False)
+    enc = enc.to(DEV)
+    from fastspeech2_lightning_b200 import ops
+
+    n0 = ops.launch_count
+    with torch.no_grad():
+        out = enc(speech.to(DEV))
+    assert ops.launch_count - n0 >= 6 + 5, "the kernel path did not run"
+    close(out, ref, 5e-5, "GST style embedding")
+    # with gradients enabled the module takes the autograd (library) path and must agree with the kernels
+    out_lib = enc(speech.to(DEV))
+    assert out_lib.requires_grad
+    close(out_lib.detach(), out, 5e-5, "kernel vs library path")
