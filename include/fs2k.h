@@ -255,6 +255,17 @@ int fs2k_gru_gate(const float* xproj, long xproj_row_stride, const float* hproj,
 int fs2k_gst_token_attention(const float* q, const float* k, const float* v, int B, int T, int heads, int dk, float* out,
                              fs2k_stream_t stream);
 
+/* ---- batch builder / prediction trimming (fs2/dataset.py:257-293, fs2/prediction_writing_callback.py:255-262; 8f rank 4)
+ * unpack_ragged: item b = rows[b] x cols[b] 4-byte words at packed + word_offsets[b] (valid values only, packed back to
+ *   back by the host into one staging buffer) -> out[B][Rmax][Cmax] words, zero padded (pad_sequence and the two-sided
+ *   padding of the [F,T] attention prior, done on the device).
+ * trim_transpose: out[out_offsets[b] + c*len_b + t] = mel[b,t,c] for t < len_b = min(lens[b], F): every utterance's valid
+ *   frames as [n_mels, T_b], packed for one D2H copy. */
+int fs2k_unpack_ragged(const void* packed_words, const long long* word_offsets, const int* rows, const int* cols, int B,
+                       int Rmax, int Cmax, void* out_words, fs2k_stream_t stream);
+int fs2k_trim_transpose(const float* mel, const int* lens, const long long* out_offsets, int B, int F, int C, float* out,
+                        fs2k_stream_t stream);
+
 /* ---- optimizer over one flat buffer (torch.optim.AdamW at fs2/model.py:530-537; clip 1.0 at fs2/cli/train.py:38) ---
  * sumsq: out[0] = Σ g² (fp64).  adamw_step: g' = g·grad_scale·min(1, max_norm/(‖g·grad_scale‖+1e-6)) when sumsq is given
  * (grad_scale = 1/world_size folds the data-parallel mean), then AdamW with decoupled weight decay and bias correction

@@ -163,3 +163,36 @@ def round_durations(log_dur: np.ndarray, control: float = 1.0) -> np.ndarray:
 
     x = torch.from_numpy(np.asarray(log_dur, dtype=np.float32))
     return torch.clamp(torch.round(torch.exp(x) - 1) * control, min=0).int().numpy()
+
+
+def collate_method(data, learn_alignment=True):
+    """Restatement of FastSpeech2DataModule.collate_method (fs2/dataset.py:257-293) for already-flat item dicts:
+    `pad_sequence(batch_first=True, padding_value=0)` for tensor keys, the two-sided zero padding of the [F_i,T_i]
+    attention prior into float32 [B,Fmax,Tmax] when `learn_alignment`, IntTensor for int keys, lens / max lens."""
+    import numpy as np
+    import torch
+    from torch.nn.utils.rnn import pad_sequence
+
+    data = {k: [dic[k] for dic in data] for k in data[0]}
+    text_lens = torch.IntTensor([text.size(0) for text in data["text"]])
+    max_text = max(text_lens)
+    if data["mel"][0] is not None:
+        mel_lens = torch.IntTensor([mel.size(0) for mel in data["mel"]])
+        max_mel = max(mel_lens)
+    else:
+        mel_lens, max_mel = None, 1_000_000
+    for key in data:
+        if isinstance(data[key][0], np.ndarray):
+            data[key] = [torch.tensor(x) for x in data[key]]
+        if torch.is_tensor(data[key][0]):
+            if key == "duration" and learn_alignment:
+                padded = torch.zeros(len(text_lens), max_mel, max_text)
+                for i, dur in enumerate(data[key]):
+                    padded[i, : dur.size(0), : dur.size(1)] = dur
+                data[key] = padded
+            else:
+                data[key] = pad_sequence(data[key], batch_first=True, padding_value=0)
+        if isinstance(data[key][0], int):
+            data[key] = torch.IntTensor(data[key])
+    data["src_lens"], data["max_src_len"], data["mel_lens"], data["max_mel_len"] = text_lens, max_text, mel_lens, max_mel
+    return data
