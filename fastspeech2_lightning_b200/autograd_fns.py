@@ -55,13 +55,17 @@ class _LayerNorm(torch.autograd.Function):
         y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True, dropout_p=p, seed=seed)
         ctx.save_for_backward(x, weight, mean, rstd)
         ctx.drop = (p, seed)
+        ctx.params = (weight, bias)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         x, weight, mean, rstd = ctx.saved_tensors
-        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight, *ctx.drop)
+        direct = _direct_grads(*ctx.params)
+        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight, *ctx.drop, accumulate_into=direct)
+        if direct is not None:
+            dw = db = None
         return dx, dw, db, None, None
 
 
@@ -88,6 +92,17 @@ class WgradSink:
         torch.cuda.current_stream().wait_stream(self.stream)
         self.keep.clear()
 
+    def fence(self):
+        """Main stream waits for what the side stream was given during the forward (transposed weights, CTC loss)."""
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def prefetch_transposed(self, w_taps):
+        """The dgrad GEMM's operand ([taps,N,K] → reversed-tap [taps,K,N]) depends on the weights only: re-pack it on
+        the side stream during the forward instead of on the critical path of the backward."""
+        self.stream.wait_stream(torch.cuda.current_stream())  # w_taps itself may just have been re-packed there
+        with torch.cuda.stream(self.stream):
+            return ops.weight_taps_transposed(w_taps)
+
 
 _SINK = None
 
@@ -99,7 +114,15 @@ def set_wgrad_sink(sink):
     return prev
 
 
-def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight=None, bias=None):
+def _direct_grads(*params):
+    """The parameters' flat-gradient views when a sink is installed and every one of them is a leaf with a .grad —
+    the backward kernels then add onto them and autograd receives None (no AccumulateGrad launch)."""
+    if _SINK is None or any(p is None or not p.is_leaf or not p.requires_grad or p.grad is None for p in params):
+        return None
+    return [p.grad for p in params]
+
+
+def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight=None, bias=None, wt=None):
     """Shared by every contraction: g = gradient w.r.t. the pre-activation conv output."""
     taps, N, K = w_taps.shape
     dx = dw = db = None
@@ -118,7 +141,7 @@ def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, we
         db = ops.colsum(g)
     with ops.backward_precision():
         if needs_x:
-            dx = ops.gemm(g, ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
+            dx = ops.gemm(g, wt if wt is not None else ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
         if needs_w:
             dw = ops.gemm_wgrad(g, x, taps, pad, conv_layout)
     return dx, dw, db
@@ -154,6 +177,7 @@ class _Gemm(torch.autograd.Function):
         ctx.save_for_backward(x, w_taps, aux)
         ctx.meta = (act, alpha, pad, conv_layout, bias is not None, residual is not None)
         ctx.params = (weight, bias)
+        ctx.wt = _SINK.prefetch_transposed(w_taps) if (_SINK is not None and ctx.needs_input_grad[0]) else None
         return y
 
     @staticmethod
@@ -164,7 +188,7 @@ class _Gemm(torch.autograd.Function):
         g = g.contiguous()
         gz = g if (act is None and alpha == 1.0 and not ctx.drop[0]) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2], *ctx.params)
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt)
         return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None, None
 
 
@@ -199,6 +223,8 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.save_for_backward(x, w_taps, z, scale, shift, mean, rstd)
         ctx.meta = (act, training, pad, bias is not None, p, seed)
         ctx.params = (weight, bias)
+        ctx.bn_params = (bn_w, bn_b)
+        ctx.wt = _SINK.prefetch_transposed(w_taps) if (_SINK is not None and ctx.needs_input_grad[0]) else None
         return y
 
     @staticmethod
@@ -206,9 +232,12 @@ class _ConvBnAct(torch.autograd.Function):
     def backward(ctx, g):
         x, w_taps, z, scale, shift, mean, rstd = ctx.saved_tensors
         act, training, pad, has_bias, p, seed = ctx.meta
-        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training, p, seed)
+        direct = _direct_grads(*ctx.bn_params)
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, act, training, p, seed, accumulate_into=direct)
+        if direct is not None:
+            dgamma = dbeta = None
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, True, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2], *ctx.params)
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt)
         return dx, dw, db, dgamma, dbeta, None, None, None, None
 
 
@@ -227,14 +256,21 @@ class _GluDwconvBnSilu(torch.autograd.Function):
         y = ops.affine_act(z, scale, shift, "silu")
         ctx.save_for_backward(h, dw_w, z, scale, shift, mean, rstd)
         ctx.training = training
+        ctx.params = (dw_w, dw_b, bn_w, bn_b)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         h, dw_w, z, scale, shift, mean, rstd = ctx.saved_tensors
-        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, "silu", ctx.training)
-        dh, ddw, ddb = ops.dwconv_bwd(gz, h, dw_w, glu=True)
+        dw_p, db_p, bnw_p, bnb_p = ctx.params
+        direct_bn, direct_dw = _direct_grads(bnw_p, bnb_p), _direct_grads(dw_p, db_p)
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous(), z, scale, shift, mean, rstd, "silu", ctx.training, accumulate_into=direct_bn)
+        dh, ddw, ddb = ops.dwconv_bwd(gz, h, dw_w, glu=True, accumulate_into=direct_dw)
+        if direct_bn is not None:
+            dgamma = dbeta = None
+        if direct_dw is not None:
+            ddw = ddb = None
         return dh, ddw, ddb, dgamma, dbeta, None, None
 
 
@@ -246,13 +282,16 @@ class _Dwconv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.params = (weight, bias)
         return ops.dwconv(x, weight, bias, channels=weight.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        return ops.dwconv_bwd(g.contiguous(), x, weight, glu=False)
+        direct = _direct_grads(*ctx.params)
+        dx, dw, db = ops.dwconv_bwd(g.contiguous(), x, weight, glu=False, accumulate_into=direct)
+        return (dx, None, None) if direct is not None else (dx, dw, db)
 
 
 def dwconv(x, weight, bias):

@@ -274,13 +274,16 @@ static int launch_dwb(const float* gz, const float* x, int ldx, int B, int L, in
 }
 
 extern "C" int fs2k_dwconv_bwd(const float* gz, const float* x, int ldx, int B, int L, int C, const float* w, int K,
-                               int glu, float* dx, float* dw, float* dbias, fs2k_stream_t stream) {
+                               int glu, float* dx, float* dw, float* dbias, int accumulate, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && C > 0 && K > 0 && (K & 1), FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(gz && x && w && dx && dw, FS2K_ERR_NULL);
     FS2K_REQUIRE(B <= 65535, FS2K_ERR_UNSUPPORTED);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * K, s);
-    if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, s);
+    cudaError_t e = cudaSuccess;
+    if (!accumulate) {  // otherwise the atomics add on top of what dw / dbias already hold
+        e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * K, s);
+        if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, s);
+    }
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (B == 0 || L == 0) return FS2K_OK;
     switch (K) {

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const double* __restrict__ sums, int act, int training, long M, int C, float drop_p,
-                    unsigned long long seed, float* __restrict__ gz, float* __restrict__ dgamma,
+                    unsigned long long seed, int accumulate, float* __restrict__ gz, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
     pdl_prologue();
     seed = seed_with_base(seed);
@@ -170,8 +170,8 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
     const float inv_m = 1.0f / (float)M;
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dbeta) dbeta[c] = (float)sums[c];
-            if (dgamma) dgamma[c] = (float)sums[C + c];
+            if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sums[c];
+            if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sums[C + c];
         }
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4) * 4;
@@ -202,14 +202,17 @@ using namespace fs2k;
 
 extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, long M, int D, float dropout_p, long seed, float* dx,
-                                  float* dgamma, float* dbeta, fs2k_stream_t stream) {
+                                  float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream) {
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((D & 3) == 0 && D <= 1024, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(g && x && mean && rstd && gamma && dx && dgamma && dbeta, FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(dgamma, 0, sizeof(float) * D, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * D, s);
+    cudaError_t e = cudaSuccess;
+    if (!accumulate) {  // otherwise the atomics add on top of what dgamma / dbeta already hold
+        e = cudaMemsetAsync(dgamma, 0, sizeof(float) * D, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * D, s);
+    }
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     if (M == 0) return FS2K_OK;
     long grid = (M + 63) / 64;  // ≥ 8 rows per warp so the per-CTA atomics amortise
@@ -225,7 +228,7 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
 extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift,
                                const float* mean, const float* rstd, int act, int training, long M, int C,
                                float dropout_p, long seed, double* sums /* [2C] scratch */, float* gz, float* dgamma,
-                               float* dbeta, fs2k_stream_t stream) {
+                               float* dbeta, int accumulate, fs2k_stream_t stream) {
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
@@ -240,7 +243,7 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     FS2K_CHECK_LAUNCH();
     long grid = (M * (C >> 2) + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    fs2k_launch(bn_bwd_apply_kernel, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, gz, dgamma, dbeta);
+    fs2k_launch(bn_bwd_apply_kernel, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, accumulate, gz, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

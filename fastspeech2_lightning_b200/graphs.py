@@ -104,6 +104,7 @@ class GraphedTrainStep:
             try:
                 out = model(batch)
                 losses = model.loss(out, batch, model.current_epoch)
+                self._sink.fence()  # transposed weights / CTC loss prepared on the side stream during the forward
                 losses["total"].backward()
             finally:
                 fns.set_wgrad_sink(prev)

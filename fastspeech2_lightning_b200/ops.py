@@ -679,28 +679,33 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=Non
     return out
 
 
-def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0):
+def _grad_targets(into, shapes, device):
+    """(buffers, accumulate): `into` = parameter-gradient tensors to add onto (contiguous fp32), or None → fresh ones."""
+    if into is not None and all(t is not None and t.is_contiguous() and t.dtype == torch.float32 for t in into):
+        return list(into), 1
+    return [torch.empty(s, dtype=torch.float32, device=device) for s in shapes], 0
+
+
+def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None):
     g, x = _f32(g, "g"), _f32(x, "x")
     D = x.shape[-1]
     M = x.numel() // D
     dx = torch.empty_like(x)
-    dgamma = torch.empty((D,), dtype=torch.float32, device=x.device)
-    dbeta = torch.empty((D,), dtype=torch.float32, device=x.device)
-    check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, float(dropout_p), int(seed), _p(dx), _p(dgamma), _p(dbeta), _stream()), "fs2k_layernorm_bwd")
+    (dgamma, dbeta), acc = _grad_targets(accumulate_into, [(D,), (D,)], x.device)
+    check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, float(dropout_p), int(seed), _p(dx), _p(dgamma), _p(dbeta), acc, _stream()), "fs2k_layernorm_bwd")
     _count()
     return dx, dgamma, dbeta
 
 
-def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: float = 0.0, seed: int = 0):
+def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None):
     g, z = _f32(g, "g"), _f32(z, "z")
     C = z.shape[-1]
     M = z.numel() // C
     sums = torch.empty((2 * C,), dtype=torch.float64, device=z.device)
     gz = torch.empty_like(z)
-    dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
-    dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
+    (dgamma, dbeta), acc = _grad_targets(accumulate_into, [(C,), (C,)], z.device)
     check(lib().fs2k_bn_act_bwd(_p(g), _p(z), _p(scale), _p(shift), _p(mean), _p(rstd), _ACTS[act], int(training), M, C,
-                                float(dropout_p), int(seed), _p(sums), _p(gz), _p(dgamma), _p(dbeta), _stream()), "fs2k_bn_act_bwd")
+                                float(dropout_p), int(seed), _p(sums), _p(gz), _p(dgamma), _p(dbeta), acc, _stream()), "fs2k_bn_act_bwd")
     _count(2)
     return gz, dgamma, dbeta
 
@@ -716,14 +721,17 @@ def attention_bwd(qkv, out, lse, dout, lens, heads: int, dropout_p: float = 0.0,
     return dqkv
 
 
-def dwconv_bwd(gz, x, weight, glu: bool, want_bias: bool = True):
+def dwconv_bwd(gz, x, weight, glu: bool, want_bias: bool = True, accumulate_into=None):
     gz, x = _f32(gz, "gz"), _f32(x, "x")
     B, L, ldx = x.shape
     C, _, K = weight.shape
     dx = torch.empty_like(x)
-    dw = torch.empty_like(weight)
-    db = torch.empty((C,), dtype=torch.float32, device=x.device) if want_bias else None
-    check(lib().fs2k_dwconv_bwd(_p(gz), _p(x), ldx, B, L, C, _p(_f32(weight)), K, int(glu), _p(dx), _p(dw), _p(db), _stream()), "fs2k_dwconv_bwd")
+    if accumulate_into is not None and want_bias:
+        (dw, db), acc = _grad_targets(accumulate_into, [tuple(weight.shape), (C,)], x.device)
+    else:
+        dw, acc = torch.empty_like(weight), 0
+        db = torch.empty((C,), dtype=torch.float32, device=x.device) if want_bias else None
+    check(lib().fs2k_dwconv_bwd(_p(gz), _p(x), ldx, B, L, C, _p(_f32(weight)), K, int(glu), _p(dx), _p(dw), _p(db), acc, _stream()), "fs2k_dwconv_bwd")
     _count()
     return dx, dw, db
 

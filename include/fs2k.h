@@ -210,23 +210,26 @@ size_t fs2k_gemm_wgrad_tc_workspace_bytes(int B, int L, int N, int K, int taps);
 int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps, int pad,
                        int passes, void* workspace, size_t workspace_bytes, float* dW_param_layout, int accumulate,
                        fs2k_stream_t stream);
-/* LayerNorm backward (dgamma/dbeta zeroed here, accumulated with atomics) */
+/* LayerNorm backward (dgamma/dbeta zeroed here unless `accumulate`, accumulated with atomics).  `accumulate` != 0 in this
+ * and in bn_act_bwd / dwconv_bwd adds the parameter gradients onto the given buffers (e.g. the flat .grad) instead. */
 int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       long M, int D, float dropout_p, long seed, float* dx, float* dgamma, float* dbeta,
-                       fs2k_stream_t stream);
+                       long M, int D, float dropout_p, long seed, float* dx, float* dgamma, float* dbeta, int accumulate,
+        fs2k_stream_t stream);
 /* BatchNorm1d (+ activation) backward: y = act(z*scale + shift), zhat = (z - mean)*rstd.
  * training: gz = scale*(gu - mean(gu) - zhat*mean(gu*zhat)); eval: gz = gu*scale; dgamma = Σ gu*zhat, dbeta = Σ gu.
  * sums: 2C doubles of scratch. */
 int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift, const float* mean,
                     const float* rstd, int act, int training, long M, int C, float dropout_p, long seed, double* sums,
-                    float* gz, float* dgamma, float* dbeta, fs2k_stream_t stream);
+                    float* gz, float* dgamma, float* dbeta, int accumulate,
+        fs2k_stream_t stream);
 /* attention backward (flash style, recomputes P from lse); delta: [B,H,L] scratch; dqkv [B,L,3·H·hd] */
 int fs2k_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, const int* lens,
                            int B, int L, int H, int head_dim, float dropout_p, long seed, float* delta, float* dqkv,
                            fs2k_stream_t stream);
 /* depthwise conv backward (glu: x = (value, gate) and dx has the same 2C layout); dw/dbias zeroed here */
 int fs2k_dwconv_bwd(const float* gz, const float* x, int ldx, int B, int L, int C, const float* w, int K, int glu,
-                    float* dx, float* dw, float* dbias, fs2k_stream_t stream);
+                    float* dx, float* dw, float* dbias, int accumulate,
+        fs2k_stream_t stream);
 int fs2k_rowdot_bwd(const float* g, const float* x, const float* w, const uint8_t* mask, long M, int D, float* dx,
                     float* dw, float* db, fs2k_stream_t stream);
 /* LengthRegulator backward: contiguous segment sums of the two output gradients (either may be NULL) */
