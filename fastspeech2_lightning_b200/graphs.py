@@ -85,6 +85,7 @@ class GraphedTrainStep:
         self.max_graphs = max_graphs
         self._cache: dict = {}
         self._seen: set = set()
+        self._eager_only: set = set()
         self._pool = None
         self.overlap_wgrad = overlap_wgrad
         self._sink = None
@@ -129,7 +130,7 @@ class GraphedTrainStep:
         key = self._key(batch)
         entry = self._cache.get(key)
         dev = opt.flat_p.device
-        if entry is None and key not in self._seen:
+        if entry is None and (key not in self._seen or key in self._eager_only):
             # first sight of this shape: plain eager step (validates the data, warms every lazy init)
             self._seen.add(key)
             dev_batch = {k: (v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
@@ -149,6 +150,14 @@ class GraphedTrainStep:
             try:
                 with torch.cuda.graph(graph, pool=self._pool):
                     static_losses = self._step_body(static_in)
+            except Exception as e:  # a library op on the path that cannot be captured (e.g. cuDNN RNN autograd of the GST encoder)
+                import warnings
+
+                warnings.warn(f"GraphedTrainStep: this step cannot be captured into a CUDA graph ({type(e).__name__}: {e}); "
+                              "running it with eager launches instead")
+                self._eager_only.add(key)
+                torch.cuda.synchronize()
+                return self(batch, non_blocking)
             finally:
                 opt.device_state = False
                 va.validate_durations = prev_validate

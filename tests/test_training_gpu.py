@@ -1,5 +1,6 @@
 """Training-step tail: flat-buffer AdamW (+ fused clipping) against torch.optim.AdamW + clip_grad_norm_,
 dropout statistics, and a short optimisation run of the whole model."""
+import numpy as np
 import pytest
 import torch
 
@@ -206,3 +207,24 @@ def test_gemm_epilogue_dropout_equals_separate_dropout_kernel():
     close(xs[0].grad, xs[1].grad, 1e-5, "dx")
     close(ws[0].grad, ws[1].grad, 1e-5, "dw")
     assert torch.equal(rs[0].grad, rs[1].grad)
+
+
+def test_optimization_step_with_gst_reference_encoder_trains():
+    """Training through the GST reference encoder uses torch autograd over library kernels (conv2d / GRU): the step must
+    still run through `optimization_step` — captured if the library ops allow it, with eager launches otherwise."""
+    import warnings
+
+    meta, _ = load_case("train_gst")
+    batch = case_batch(meta, DEV)
+    model = _fresh_model(meta)
+    model.train()  # cuDNN's RNN backward exists in training mode only
+    before = model.optimizer.flat_p.clone()
+    losses = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(4):
+            losses.append(float(model.optimization_step(batch)["total"]))
+    assert all(np.isfinite(v) for v in losses), losses  # (dropout is on: four steps are too noisy to demand a decrease)
+    assert model.optimizer._step == 4 and bool(torch.isfinite(model.optimizer.flat_p).all())
+    gst = [p for n, p in model.named_parameters() if n.startswith("gst.ref_enc")]
+    assert float((model.optimizer.flat_p - before).abs().max()) > 0 and all(float(p.grad.abs().max()) > 0 for p in gst)
