@@ -102,7 +102,7 @@ constexpr int TC_EPI_WARPS = 8;                 // warps 4..11: operand split (3
 constexpr int TC_WARPS = TC_THREADS / 32;       // 12
 constexpr int TC_ROWS_PER_ITER = 4;             // rows a warp keeps in flight in the store pass
 
-template <int PASSES>
+template <int PASSES, bool DROPOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
@@ -242,8 +242,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int rows_valid = (int)min((long)TC_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
         const float inv_n = 1.0f / (float)block_n;
-        const float drop_p = ep.drop_p, inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
-        const unsigned long long seed = drop_p > 0.f ? seed_with_base(ep.seed) : 0ull;
+        // (DROPOUT is a template flag: the counter hash must not sit in the store loop of the launches that never drop)
+        const float drop_p = DROPOUT ? ep.drop_p : 0.f, inv_keep = DROPOUT ? 1.0f / (1.0f - drop_p) : 1.f;
+        const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         for (int rb = warp; rb < rows_valid; rb += TC_WARPS * TC_ROWS_PER_ITER) {
             float4 val[TC_ROWS_PER_ITER][2], res[TC_ROWS_PER_ITER][2];
             float rm[TC_ROWS_PER_ITER];
@@ -273,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int qv = lane + 32 * j;
                         float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
                         v = tc_colmath(v, bias4[j], sc4[j], sh4[j], ep.act, ep.alpha);
-                        if (drop_p > 0.f) {
+                        if (DROPOUT) {
                             const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
                             v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
                             v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
@@ -422,15 +423,16 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     dim3 grid(Bm * tiles_per_b, N / block_n);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    if (passes == 3) {
-        e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(gemm_tc_kernel<3>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
-    } else {
-        e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
-    }
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        fs2k_launch(kernel, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
+        return cudaSuccess;
+    };
+    const bool drop = dropout_p > 0.f;
+    if (passes == 3) e = drop ? launch(gemm_tc_kernel<3, true>) : launch(gemm_tc_kernel<3, false>);
+    else e = drop ? launch(gemm_tc_kernel<1, true>) : launch(gemm_tc_kernel<1, false>);
+    if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
