@@ -102,7 +102,7 @@ constexpr int TC_EPI_WARPS = 8;                 // warps 4..11: operand split (3
 constexpr int TC_WARPS = TC_THREADS / 32;       // 12
 constexpr int TC_ROWS_PER_ITER = 4;             // rows a warp keeps in flight in the store pass
 
-template <int PASSES, bool DROPOUT>
+template <int PASSES, bool DROPOUT, bool LNORM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
@@ -235,10 +235,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bias4[j] = (has[j] && ep.bias) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + qv) : zero4;
             sc4[j] = (has[j] && ep.scale) ? __ldg(reinterpret_cast<const float4*>(ep.scale + n0) + qv) : one4;
             sh4[j] = (has[j] && ep.scale) ? __ldg(reinterpret_cast<const float4*>(ep.shift + n0) + qv) : zero4;
-            g1[j] = (has[j] && ep.ln_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + qv) : one4;
-            b1[j] = (has[j] && ep.ln_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + qv) : zero4;
-            g2[j] = (has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma) + qv) : one4;
-            b2[j] = (has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_beta) + qv) : zero4;
+            g1[j] = (LNORM && has[j]) ? __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + qv) : one4;
+            b1[j] = (LNORM && has[j]) ? __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + qv) : zero4;
+            g2[j] = (LNORM && has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma) + qv) : one4;
+            b2[j] = (LNORM && has[j] && ep.ln2_out) ? __ldg(reinterpret_cast<const float4*>(ep.ln2_beta) + qv) : zero4;
         }
         const int rows_valid = (int)min((long)TC_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
         const float inv_n = 1.0f / (float)block_n;
@@ -283,14 +283,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
                         v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];
-                        if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
-                        val[u][j] = v;
-                        sum += tc_sum4(v);
-                    } else {
+                        if (!LNORM || ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
+                        if (LNORM) {
+                            val[u][j] = v;
+                            sum += tc_sum4(v);
+                        }
+                    } else if (LNORM) {
                         val[u][j] = zero4;
                     }
                 }
-                if (ep.ln_out) {  // LayerNorm over the block_n == N columns of this row (one warp holds the row)
+                if (LNORM) {  // LayerNorm over the block_n == N columns of this row (one warp holds the row)
                     float mean = warp_sum(sum) * inv_n;
                     float ss = 0.f;
 #pragma unroll
@@ -430,8 +432,10 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
         return cudaSuccess;
     };
     const bool drop = dropout_p > 0.f;
-    if (passes == 3) e = drop ? launch(gemm_tc_kernel<3, true>) : launch(gemm_tc_kernel<3, false>);
-    else e = drop ? launch(gemm_tc_kernel<1, true>) : launch(gemm_tc_kernel<1, false>);
+    FS2K_REQUIRE(!(drop && ln_out), FS2K_ERR_UNSUPPORTED);
+    if (ln_out) e = passes == 3 ? launch(gemm_tc_kernel<3, false, true>) : launch(gemm_tc_kernel<1, false, true>);
+    else if (passes == 3) e = drop ? launch(gemm_tc_kernel<3, true, false>) : launch(gemm_tc_kernel<3, false, false>);
+    else e = drop ? launch(gemm_tc_kernel<1, true, false>) : launch(gemm_tc_kernel<1, false, false>);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
