@@ -24,7 +24,9 @@ int fs2k_set_cuda_error(cudaError_t e);
 // CTA of this one has executed griddepcontrol.launch_dependents — which every kernel does first thing — and
 // then blocks in griddepcontrol.wait until this grid has completed and its writes are visible.  Launch latency
 // and kernel prologues (barrier init, TMEM allocation, parameter loads) overlap the tail of the previous kernel;
-// nothing that reads or writes global memory runs before the wait.  fs2k_set_pdl(0) switches the attribute off.
+// nothing that reads or writes global memory runs before the wait.  Exception: the small, long, latency-bound
+// grids (MAS DP, CTC recursions: one CTA per utterance) use fs2k_launch_serial and never trigger early (see below).
+// fs2k_set_pdl(0) = attribute off everywhere.
 extern int g_fs2k_pdl_enabled;  // lib.cu
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -35,8 +37,8 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 template <typename... KArgs, typename... Args>
-static inline void fs2k_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                               Args&&... args) {
+static inline void fs2k_launch_impl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -46,8 +48,21 @@ static inline void fs2k_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_fs2k_pdl_enabled ? 1 : 0;
+    cfg.numAttrs = (pdl && g_fs2k_pdl_enabled) ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in FS2K_CHECK_LAUNCH
+}
+template <typename... KArgs, typename... Args>
+static inline void fs2k_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
+    fs2k_launch_impl(true, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+// Plain stream-ordered launch for the small latency-bound grids (one CTA per utterance: MAS DP, CTC recursions).
+// Launched programmatically they are placed while the previous kernel still fills the machine, several CTAs end up on
+// the same SM instead of one per SM, and the serial recursion runs 2.6x slower (measured on the MAS DP at B = 32).
+template <typename... KArgs, typename... Args>
+static inline void fs2k_launch_serial(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args&&... args) {
+    fs2k_launch_impl(false, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

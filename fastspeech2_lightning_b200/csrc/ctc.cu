@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(CTC_THREADS)
 ctc_alpha_kernel(const float* __restrict__ logit, const int* __restrict__ key_lens, const int* __restrict__ query_lens,
                  int F, int T, float blank, double* __restrict__ lse_out, double* __restrict__ log_alpha,
                  double* __restrict__ nll_out) {
-    pdl_prologue();
+    pdl_wait();  // launched with fs2k_launch_serial (one CTA per SM matters here) and never triggers its dependents early
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int K = min(max(key_lens[b], 0), T), Q = min(max(query_lens[b], 0), F);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(CTC_THREADS)
 ctc_beta_grad_kernel(const float* __restrict__ logit, const double* __restrict__ lse_g, const double* __restrict__ log_alpha,
                      const double* __restrict__ nll_g, const int* __restrict__ key_lens, const int* __restrict__ query_lens,
                      const float* __restrict__ gout, int B, int F, int T, float blank, float* __restrict__ dlogit) {
-    pdl_prologue();
+    pdl_wait();  // launched with fs2k_launch_serial (one CTA per SM matters here) and never triggers its dependents early
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int K = min(max(key_lens[b], 0), T), Q = min(max(query_lens[b], 0), F);
@@ -191,7 +191,7 @@ extern "C" int fs2k_ctc_forward_sum_fwd(const float* attn_logprob, const int* ke
             cudaError_t e = cudaFuncSetAttribute(ctc_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fs2k_set_cuda_error(e);
         }
-        fs2k_launch(ctc_alpha_kernel, dim3(B), dim3(CTC_THREADS), smem, s, attn_logprob, key_lens, query_lens, F, T, blank_logprob, lse, log_alpha, nll);
+        fs2k_launch_serial(ctc_alpha_kernel, dim3(B), dim3(CTC_THREADS), smem, s, attn_logprob, key_lens, query_lens, F, T, blank_logprob, lse, log_alpha, nll);
         FS2K_CHECK_LAUNCH();
     }
     fs2k_launch(ctc_finalize_kernel, dim3(1), dim3(1), 0, s, nll, key_lens, B, T, loss);
@@ -211,7 +211,7 @@ extern "C" int fs2k_ctc_forward_sum_bwd(const float* attn_logprob, const double*
         cudaError_t e = cudaFuncSetAttribute(ctc_beta_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     }
-    fs2k_launch(ctc_beta_grad_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, attn_logprob, lse, log_alpha, nll, key_lens, query_lens,
+    fs2k_launch_serial(ctc_beta_grad_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, attn_logprob, lse, log_alpha, nll, key_lens, query_lens,
                                                                          gout, B, F, T, blank_logprob, d_attn_logprob);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

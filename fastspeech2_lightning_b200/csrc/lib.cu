@@ -42,7 +42,7 @@ extern "C" int fs2k_check_device(void) {
 // Occupies the stream for `ns` nanoseconds (bench.py's roofline pass queues work behind it so that the
 // per-kernel CUDA-event timings that follow are not stretched by host launch gaps).
 __global__ void spin_kernel(unsigned long long ns) {
-    pdl_launch_dependents();
+    pdl_wait();
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {

@@ -45,7 +45,7 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
               int* __restrict__ path,            // [B,F] column of frame f, −1 on padding
               int* __restrict__ durations)       // [B,T]
 {
-    pdl_prologue();
+    pdl_wait();  // launched with fs2k_launch_serial (one CTA per SM matters here) and never triggers its dependents early
     extern __shared__ float ring[];  // [PF][CHUNKS·blockDim] then uint32 sdir[MAS_DB][W]
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
@@ -205,7 +205,7 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
         cudaError_t e = cudaFuncSetAttribute(mas_dp_kernel<CHUNKS, PF, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    fs2k_launch(mas_dp_kernel<CHUNKS, PF, LOG>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
+    fs2k_launch_serial(mas_dp_kernel<CHUNKS, PF, LOG>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
     return cudaGetLastError();
 }
 

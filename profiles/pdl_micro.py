@@ -28,3 +28,32 @@ for name, fn in (("tanh x200", chain_small), ("gemm x50", chain_gemm)):
         for _ in range(20): g.replay()
         e.record(); torch.cuda.synchronize()
         print(name, "pdl", pdl, "ms per replay", s.elapsed_time(e) / 20)
+
+# eager (no graph) launch cost with / without the PDL attribute
+import time
+for pdl in (1, 0, 1, 0):
+    _lib.lib().fs2k_set_pdl(pdl)
+    chain_small(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5):
+        chain_small()
+    e.record(); torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print("eager tanh x1000 pdl", pdl, "device us/kernel", s.elapsed_time(e), "host us/kernel", (t1 - t0) * 1e6 / 1000)
+# a memset between kernels (what fs2k_mas_fwd / fs2k_colsum do)
+for pdl in (1, 0):
+    _lib.lib().fs2k_set_pdl(pdl)
+    z = torch.randn(4096, 256, device="cuda")
+    ops.colsum(z); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(100):
+            ops.colsum(z)
+    g.replay(); torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10): g.replay()
+    e.record(); torch.cuda.synchronize()
+    print("graph memset+colsum x100 pdl", pdl, "us per pair", s.elapsed_time(e) * 1000 / 1000)
