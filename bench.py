@@ -52,6 +52,20 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(workload: str, entry_point: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel behind `entry_point`, from the
+    committed ncu pass of the same workload (profiles/r1_summary_<workload>_v3.json, made by profiles/summarize_launches.py
+    from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`); None when there is none."""
+    f = ROOT / "profiles" / f"r1_summary_{workload}_v3.json"
+    names = {"fs2k_gemm_tc": "gemm_tc_kernel", "fs2k_mas_fwd": "mas_dp_kernel", "fs2k_attention_f32": "attention_simt_kernel"}
+    if not f.exists() or entry_point not in names:
+        return None
+    for k in json.loads(f.read_text())["by_kernel"]:
+        if k["kernel"].endswith(names[entry_point]):
+            return k["dram_bytes_per_launch"]
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -242,8 +256,9 @@ def run_ours(args, wl_name, wl, rank, world, device):
         roof = {"kernel": dom, "bound": "tensor", "achieved": d[1] / (d[0] * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=pk["source"], share_of_step=d[0] / tot_ms,
-                launches=d[3], shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])})
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(wl_name, dom), peak_source=pk["source"], share_of_step=d[0] / tot_ms,
+                launches=d[3], algorithmic_bytes_per_launch=d[2] / d[3],
+                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])})
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
@@ -373,8 +388,9 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         roof = {"kernel": dom, "bound": "tensor", "achieved": d[1] / (d[0] * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=pk["source"], share_of_step=d[0] / tot_ms,
-                launches=d[3], shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]})
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(wl_name, dom), peak_source=pk["source"], share_of_step=d[0] / tot_ms,
+                launches=d[3], algorithmic_bytes_per_launch=d[2] / d[3],
+                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]})
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
     if world > 1:
