@@ -5,6 +5,7 @@
 namespace fs2k {
 
 constexpr int kDwbTile = 32;
+constexpr int kDwbUnroll = 4;
 
 // gz [B,L,C] → dx (GLU: [B,L,2C] = (d value, d gate)), dw [C][K] (+=), dbias [C] (+=)
 template <int K, bool GLU>
@@ -34,25 +35,43 @@ dwconv_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ x, int
 #pragma unroll
     for (int k = 0; k < K - 1; ++k) { gwin[k + 1] = fetch_g(l0 - P + k); awin[k + 1] = fetch_a(l0 - P + k); }
     const int l_end = min(l0 + kDwbTile, L);
-    for (int l = l0; l < l_end; ++l) {
+    // kDwbUnroll frames per trip: all their loads are issued before any is consumed (a one-load-per-step loop exposes
+    // the L2 latency on every frame)
+    for (int l = l0; l < l_end; l += kDwbUnroll) {
+        float ng[kDwbUnroll], na[kDwbUnroll], vv[kDwbUnroll], gt[kDwbUnroll];
 #pragma unroll
-        for (int k = 0; k < K - 1; ++k) { gwin[k] = gwin[k + 1]; awin[k] = awin[k + 1]; }
-        gwin[K - 1] = fetch_g(l + P);
-        awin[K - 1] = fetch_a(l + P);
-        float da = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            da = fmaf(gwin[k], wk[K - 1 - k], da);        // dL/da[l] = Σ_k gz[l+P−k]·w[k]
-            dwk[k] = fmaf(gwin[P], awin[k], dwk[k]);      // dL/dw[k] += gz[l]·a[l+k−P]
+        for (int u = 0; u < kDwbUnroll; ++u) {
+            const bool ok = l + u < l_end;
+            ng[u] = ok ? fetch_g(l + u + P) : 0.f;
+            na[u] = ok ? fetch_a(l + u + P) : 0.f;
+            vv[u] = gt[u] = 0.f;
+            if (GLU && ok) {
+                vv[u] = xb[(size_t)(l + u) * ldx + c];
+                gt[u] = xb[(size_t)(l + u) * ldx + C + c];
+            }
         }
-        db += gwin[P];
-        if (GLU) {
-            const float v = xb[(size_t)l * ldx + c], gt = xb[(size_t)l * ldx + C + c];
-            const float sg = 1.0f / (1.0f + expf(-gt));
-            dx[((size_t)b * L + l) * ldx + c] = da * sg;
-            dx[((size_t)b * L + l) * ldx + C + c] = da * v * sg * (1.0f - sg);
-        } else {
-            dx[((size_t)b * L + l) * ldx + c] = da;
+#pragma unroll
+        for (int u = 0; u < kDwbUnroll; ++u) {
+            if (l + u >= l_end) break;  // CTA-uniform
+#pragma unroll
+            for (int k = 0; k < K - 1; ++k) { gwin[k] = gwin[k + 1]; awin[k] = awin[k + 1]; }
+            gwin[K - 1] = ng[u];
+            awin[K - 1] = na[u];
+            float da = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                da = fmaf(gwin[k], wk[K - 1 - k], da);        // dL/da[l] = Σ_k gz[l+P−k]·w[k]
+                dwk[k] = fmaf(gwin[P], awin[k], dwk[k]);      // dL/dw[k] += gz[l]·a[l+k−P]
+            }
+            db += gwin[P];
+            const size_t o = ((size_t)b * L + l + u) * ldx;
+            if (GLU) {
+                const float sg = 1.0f / (1.0f + expf(-gt[u]));
+                dx[o + c] = da * sg;
+                dx[o + C + c] = da * vv[u] * sg * (1.0f - sg);
+            } else {
+                dx[o + c] = da;
+            }
         }
     }
 #pragma unroll
