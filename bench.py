@@ -408,7 +408,9 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
                                f"duration/pitch/energy/mel/postnet/CTC/bin losses, backward, clip 1.0, AdamW+Noam), B={B}/GPU, T<={T}, F<={F}",
                    "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}: per-rank replicas, one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "dp1",
-                   "launch": "cuda graph replay of the whole step (zero_grad, forward, losses, backward, clip, AdamW), one graph per batch shape"
+                   "launch": ("cuda graph replay of the whole step (zero_grad, forward, losses, backward, clip, AdamW), one graph per batch shape"
+                              if world == 1 else
+                              "two cuda graph replays per step (zero_grad+forward+losses+backward | clip+AdamW) around the eager NCCL all-reduce")
                              if graphs else "eager (one launch per kernel)"},
         "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e / args.steps, "api": "FastSpeech2.optimization_step (training_step + backward + clip + FusedAdamW.step + NoamLR.step)"},

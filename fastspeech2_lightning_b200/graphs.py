@@ -68,8 +68,8 @@ class GraphedSynthesis:
 
 class GraphedTrainStep:
     """One optimisation step — zero_grad, forward (aligner + MAS + encoder + variance adaptor + decoder + PostNet),
-    the seven losses, backward, (NCCL all-reduce of the flat gradient), clip and AdamW — as ONE CUDA graph per batch
-    shape: ≈1000 kernel launches become one `cudaGraphLaunch`, so a step costs what the GPU needs, not what Python
+    the seven losses, backward, clip and AdamW — as ONE CUDA graph per batch shape (data-parallel runs: a
+    forward/backward graph, the NCCL all-reduce of the flat gradient launched eagerly, and an update graph): ≈1000 kernel launches become one `cudaGraphLaunch`, so a step costs what the GPU needs, not what Python
     can enqueue.
 
     Everything that changes between steps lives in device memory: the batch (copied into the captured input
@@ -91,7 +91,7 @@ class GraphedTrainStep:
         self._sink = None
         lib().fs2k_set_dropout_seed_base(optimizer.seed_base.data_ptr())
 
-    def _step_body(self, batch):
+    def _step_body(self, batch, update: bool = True):
         from . import autograd_fns as fns
 
         model, opt = self.model, self.opt
@@ -114,7 +114,8 @@ class GraphedTrainStep:
             out = model(batch)
             losses = model.loss(out, batch, model.current_epoch)
             losses["total"].backward()
-        opt.step()
+        if update:
+            opt.step()
         # detached: a loss that kept its autograd graph alive would also keep this step's AccumulateGrad nodes (and
         # their stream) alive into the next capture
         return {k: v.detach() for k, v in losses.items()}
@@ -146,10 +147,17 @@ class GraphedTrainStep:
             prev_validate, va.validate_durations = va.validate_durations, False  # the eager first sight validated
             opt.device_state = True
             torch.cuda.synchronize()
+            # data-parallel: the NCCL all-reduce stays OUTSIDE the graphs (forward/backward graph → eager all-reduce →
+            # update graph); single GPU: one graph for everything
+            split = opt.world_size() > 1
             graph = torch.cuda.CUDAGraph()
+            graph2 = torch.cuda.CUDAGraph() if split else None
             try:
                 with torch.cuda.graph(graph, pool=self._pool):
-                    static_losses = self._step_body(static_in)
+                    static_losses = self._step_body(static_in, update=not split)
+                if split:
+                    with torch.cuda.graph(graph2, pool=graph.pool()):
+                        opt.step(allreduce=False)
             except Exception as e:  # a library op on the path that cannot be captured (e.g. cuDNN RNN autograd of the GST encoder)
                 import warnings
 
@@ -163,14 +171,17 @@ class GraphedTrainStep:
                 va.validate_durations = prev_validate
             if self._pool is None:
                 self._pool = graph.pool()
-            entry = (graph, static_in, static_losses)
+            entry = (graph, static_in, static_losses, graph2)
             self._cache[key] = entry
-        graph, static_in, static_losses = entry
+        graph, static_in, static_losses, graph2 = entry
         for k, v in batch.items():
             if torch.is_tensor(v) and v.dim() > 0:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         opt.begin_graph_step()
         graph.replay()
+        if graph2 is not None:
+            opt.allreduce_grads()
+            graph2.replay()
         if self.sched is not None:
             self.sched.step()
         return static_losses

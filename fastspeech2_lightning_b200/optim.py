@@ -65,14 +65,23 @@ class FusedAdamW(torch.optim.Optimizer):
         ops._count()
         return self._sumsq.sqrt()
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = closure() if closure is not None else None
-        world = 1
+    def world_size(self) -> int:
         if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.process_group)
-            if world > 1:  # data-parallel exchange: one all-reduce of the flat gradient; the mean folds into the update
-                torch.distributed.all_reduce(self.flat_g, group=self.process_group)
+            return torch.distributed.get_world_size(self.process_group)
+        return 1
+
+    @torch.no_grad()
+    def allreduce_grads(self) -> None:
+        """The data-parallel exchange: one (sum) all-reduce of the flat gradient; the 1/world mean folds into the update."""
+        if self.world_size() > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.process_group)
+
+    @torch.no_grad()
+    def step(self, closure=None, allreduce: bool = True):
+        loss = closure() if closure is not None else None
+        world = self.world_size()
+        if world > 1 and allreduce:
+            self.allreduce_grads()
         g = self.param_groups[0]
         stream = torch.cuda.current_stream().cuda_stream
         sumsq = None
