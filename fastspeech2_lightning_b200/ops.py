@@ -262,13 +262,18 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
     # keyed on the tensor OBJECT (weak reference): id()/data_ptr()/_version alone can all be reused by a new
     # parameter allocated at a freed one's address, which would hand back another model's weights
     key = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    hit = _repack_cache.get(id(weight))
+    # while a CUDA graph is being captured the re-pack must be a node of the graph (the weights change between replays)
+    # and its output lives in the graph's pool: neither read nor fill the cache then
+    capturing = weight.is_cuda and torch.cuda.is_current_stream_capturing()
+    hit = None if capturing else _repack_cache.get(id(weight))
     if hit is not None and hit[0] == key and hit[2]() is weight:
         return hit[1]
     w = _f32(weight.detach(), "weight")
     out = torch.empty((taps, N, K), dtype=torch.float32, device=w.device)
     check(lib().fs2k_repack_conv_weight(_p(w), N, K, taps, _p(out), _stream()), "fs2k_repack_conv_weight")
     _count()
+    if capturing:
+        return out
     if len(_repack_cache) > 512:  # drop entries whose parameter is gone
         for k in [k for k, v in _repack_cache.items() if v[2]() is None]:
             del _repack_cache[k]

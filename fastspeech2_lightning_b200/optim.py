@@ -65,6 +65,11 @@ class FusedAdamW(torch.optim.Optimizer):
         ops._count()
         return self._sumsq.sqrt()
 
+    def _bump_versions(self) -> None:
+        """The update kernel writes the parameters through raw pointers, which torch's version counters do not see:
+        bump them, so that anything cached per parameter version (the re-packed conv weights in ops) is refreshed."""
+        torch.autograd.graph.increment_version(self._params)
+
     def world_size(self) -> int:
         if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             return torch.distributed.get_world_size(self.process_group)
@@ -97,6 +102,7 @@ class FusedAdamW(torch.optim.Optimizer):
             ops._count()
             return loss
         self._step += 1
+        self._bump_versions()
         if self.max_grad_norm is not None:
             check(lib().fs2k_sumsq(self.flat_g.data_ptr(), self.flat_g.numel(), self._sumsq.data_ptr(), stream), "fs2k_sumsq")
             ops._count()
@@ -114,6 +120,7 @@ class FusedAdamW(torch.optim.Optimizer):
         corrections and a fresh dropout seed base to the device (one tiny launch, arguments by value)."""
         g = self.param_groups[0]
         self._step += 1
+        self._bump_versions()
         self._opt_called = True  # LRScheduler's "scheduler.step() before optimizer.step()" check
         b1, b2 = g["betas"]
         seed = int(torch.randint(0, 2**62, (1,)).item())

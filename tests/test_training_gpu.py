@@ -228,3 +228,69 @@ def test_optimization_step_with_gst_reference_encoder_trains():
     assert model.optimizer._step == 4 and bool(torch.isfinite(model.optimizer.flat_p).all())
     gst = [p for n, p in model.named_parameters() if n.startswith("gst.ref_enc")]
     assert float((model.optimizer.flat_p - before).abs().max()) > 0 and all(float(p.grad.abs().max()) > 0 for p in gst)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_repacked_conv_weights_follow_the_optimizer(graph):
+    """The update kernel writes parameters through raw pointers; everything cached per parameter version (the
+    [N,K,taps] → [taps,N,K] re-pack of Conv1d weights) must still see the new values — eagerly and inside replays."""
+    from fastspeech2_lightning_b200 import ops
+
+    meta, _ = load_case("train_bn")
+    batch = case_batch(meta, DEV)
+    model = _fresh_model(meta)
+    model.scheduler.base_lrs = [1.0 for _ in model.scheduler.base_lrs]  # Noam: lr = 2.5e-4·step — visible updates
+    w = next(p for n, p in model.named_parameters() if n.startswith("postnet") and p.dim() == 3 and p.shape[-1] > 1)
+    before = w.detach().clone()
+    first = ops.conv_weight_taps(w).clone()
+    steps = 4 if graph else 2
+    for _ in range(steps):
+        model.optimization_step(batch, use_cuda_graph=graph)
+    assert float((w.detach() - before).abs().max()) > 1e-5  # the optimizer moved it
+    now = ops.conv_weight_taps(w)
+    assert torch.equal(now, w.detach().permute(2, 0, 1).contiguous()), "stale re-packed conv weight"
+    assert not torch.equal(now, first)
+
+
+def test_three_optimisation_steps_follow_the_oracle_with_torch_adamw():
+    """End-to-end training parity over several steps: kernels + FusedAdamW + NoamLR on the GPU against the oracle's
+    forward/loss with torch autograd, clip_grad_norm_(1.0), torch.optim.AdamW and the same schedule on the CPU.
+    Dropout is off (golden `train_bn` configuration).  A forward that kept using old weights would drift by percents."""
+    from fastspeech2_lightning_b200.fs2.noam import NoamLR
+    from helpers import case_config, case_state_dict
+    from oracle import fs2_oracle
+
+    meta, _ = load_case("train_bn")
+    cfg = case_config(meta)
+    model = _fresh_model(meta)
+    o = cfg.training.optimizer
+    sd = {k: v.clone() for k, v in case_state_dict(meta).items()}
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "_bins", "inv_freq")):
+            v.requires_grad_(True)
+            params.append(v)
+    ref_opt = torch.optim.AdamW(params, lr=o.learning_rate, betas=tuple(o.betas), eps=o.eps, weight_decay=o.weight_decay)
+    ref_sched = NoamLR(ref_opt, o.warmup_steps)
+    for s in (model.scheduler, ref_sched):
+        s.base_lrs = [1.0 for _ in s.base_lrs]  # lr = 2.5e-4·step: three visible updates
+    for g, gr in zip(model.optimizer.param_groups, ref_opt.param_groups):
+        g["lr"] = gr["lr"] = 2.5e-4
+    ocfg = fs2_oracle.Cfg(cfg)
+    batch_cpu = case_batch(meta, "cpu")
+    batch = case_batch(meta, DEV)
+    got, want = [], []
+    for step in range(3):
+        got.append(float(model.optimization_step(batch, use_cuda_graph=False)["total"]))
+        ref_opt.zero_grad()
+        out = fs2_oracle.forward(sd, ocfg, batch_cpu, training=True, new_stats={})
+        loss = fs2_oracle.loss(out, batch_cpu, ocfg, model.current_epoch)["total"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        ref_opt.step()
+        ref_sched.step()
+        want.append(float(loss.detach()))
+    print("loss trajectory gpu", got, "oracle", want)
+    assert abs(want[2] - want[0]) > 1e-3 * abs(want[0]), "the steps did not change the loss: the test would prove nothing"
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 2e-4 * abs(b), (got, want)
