@@ -601,7 +601,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--also", default="synth_c1,mas_c2", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
+    ap.add_argument("--also", default="synth_c1,synth_c1@dec-tf32,mas_c2", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
@@ -632,12 +632,19 @@ def main():
 
         line["also"] = {}
         for entry in [n for n in args.also.split(",") if n and n != args.workload]:
-            name, _, prec = entry.partition("@")  # "synth_c1@tf32": the same workload in the single-pass fast mode
+            # "synth_c1@tf32": the same workload in single-pass TF32; "synth_c1@dec-tf32": only the decoder / PostNet
+            # (everything after the last discrete decision) in single-pass TF32 — the reduced-precision configuration
+            name, _, prec = entry.partition("@")
             a2 = copy.copy(args)
             a2.no_cpu_baseline = True
             a2.steps = min(args.steps, 10)
-            _ops.set_precision(prec or args.precision, args.backward_precision)
+            if prec.startswith("dec-"):
+                _ops.set_precision(args.precision, args.backward_precision, decoder=prec[4:])
+            else:
+                _ops.set_precision(prec or args.precision, args.backward_precision)
             sub = run_ours(a2, name, WORKLOADS[name], rank, world, device)
+            if prec:
+                sub["dtype"] = f"{sub.get('dtype')} / decoder+postnet {prec[4:]} (reduced-precision mode, mel L1 <= 1e-2)" if prec.startswith("dec-") else sub.get("dtype")
             _ops.set_precision(args.precision, args.backward_precision)
             line["also"][entry] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "config", "dtype") if k in sub}
     if rank == 0:

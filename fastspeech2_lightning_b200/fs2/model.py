@@ -201,11 +201,12 @@ class FastSpeech2(_Base):
             dec_in = va["output_with_pos"]
         else:
             dec_in = fns.add_posenc(va["output"], inv_freq, ops.mask_lens(tgt_mask))
-        x, _ = self.decoder(dec_in, mel_lens)
-        output = ag.linear(x, self.mel_linear.weight, self.mel_linear.bias)
-        postnet_output = None
-        if m.use_postnet:
-            postnet_output = fns.add(output, self.postnet(output))
+        with ops.decoder_precision():  # no discrete decision follows: optional reduced-precision synthesis (ops.set_precision)
+            x, _ = self.decoder(dec_in, mel_lens)
+            output = ag.linear(x, self.mel_linear.weight, self.mel_linear.bias)
+            postnet_output = None
+            if m.use_postnet:
+                postnet_output = fns.add(output, self.postnet(output))
         return {
             "output": output,
             "postnet_output": postnet_output,

@@ -292,13 +292,35 @@ PRECISION = "tf32x3"
 BACKWARD_PRECISION = None
 
 
-def set_precision(mode: str, backward: str | None = None) -> None:
-    global PRECISION, BACKWARD_PRECISION
-    for m in (mode, backward):
+# Synthesis only: arithmetic of the contractions AFTER the last discrete decision (decoder, mel_linear, PostNet); None =
+# same as PRECISION.  "tf32" there is the reduced-precision configuration north_star allows (mel L1 ≤ 1e-2): bucket ids,
+# durations and the length regulator are still decided in fp32-level arithmetic, so nothing flips — only the mel carries
+# the ≈1e-3 relative TF32 rounding.
+DECODER_PRECISION = None
+
+
+def set_precision(mode: str, backward: str | None = None, decoder: str | None = None) -> None:
+    global PRECISION, BACKWARD_PRECISION, DECODER_PRECISION
+    for m in (mode, backward, decoder):
         if m not in (None, "fp32", "tf32", "tf32x3"):
             raise ValueError(m)
     PRECISION = mode
     BACKWARD_PRECISION = backward
+    DECODER_PRECISION = decoder
+
+
+class decoder_precision:
+    """Context for the synthesis decoder / mel_linear / PostNet: DECODER_PRECISION when set and no gradient is needed."""
+
+    def __enter__(self):
+        global PRECISION
+        self.prev = PRECISION
+        if DECODER_PRECISION is not None and not torch.is_grad_enabled():
+            PRECISION = DECODER_PRECISION
+
+    def __exit__(self, *a):
+        global PRECISION
+        PRECISION = self.prev
 
 
 class backward_precision:

@@ -215,3 +215,28 @@ def test_gst_style_encoder_kernels_match_the_oracle(B, F):
     out_lib = enc(speech.to(DEV))
     assert out_lib.requires_grad
     close(out_lib.detach(), out, 5e-5, "kernel vs library path")
+
+
+def test_reduced_precision_decoder_mode_meets_the_mel_l1_bar():
+    """`ops.set_precision("tf32x3", decoder="tf32")`: everything up to the last discrete decision (bucket ids, durations,
+    length regulator) stays in fp32-level arithmetic, the decoder / mel_linear / PostNet run single-pass TF32.  north_star's
+    bar for the reduced-precision configuration is mel L1 ≤ 1e-2 against the reference; integers stay exact."""
+    from fastspeech2_lightning_b200 import ops
+
+    for name in ("infer_tf", "infer_free"):
+        meta, gold = load_case(name)
+        model = build_model(meta)
+        batch = case_batch(meta, DEV)
+        ops.set_precision("tf32x3", decoder="tf32")
+        try:
+            with torch.no_grad():
+                out = model(batch, inference=True)
+        finally:
+            ops.set_precision("tf32x3")
+        assert torch.equal(out["tgt_lens"].cpu().long(), torch.from_numpy(gold["out.tgt_lens"]).long())
+        for k in ("output", "postnet_output"):
+            ref = torch.from_numpy(gold["out." + k])
+            l1 = float((out[k].cpu() - ref).abs().mean())
+            print(f"{name}: decoder in single-pass TF32, mel L1 of {k} = {l1:.2e} (mean |mel| {float(ref.abs().mean()):.2f})")
+            assert l1 <= 1e-2, (name, k, l1)
+            assert l1 > 1e-7  # the mode is really active
