@@ -164,7 +164,7 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                     float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    constexpr int BKEY = 64, BQ = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
+    constexpr int BKEY = 64, BQ = 64, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Ks = smem;               // [BKEY][QS]
     float* Vs = Ks + BKEY * QS;     // [BKEY][QS]
@@ -214,40 +214,39 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                 s_del[tid] = q < L ? delta[((size_t)b * H + h) * L + q] : 0.f;
             }
             __syncthreads();
-            // S, dP for 2 queries (ty*2..+1) × 4 keys (tx + 16j)
-            float s[2][4], dp[2][4];
+            // S, dP for 4 queries (ty*4..+3) × 4 keys (tx + 16j): 24 shared-memory wavefronts per 128 FFMA (the 2×4
+            // tile this replaces needed 20 per 64 and was bound by the LDS pipe)
+            float s[4][4], dp[4][4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
-#pragma unroll 4
+#pragma unroll 2
             for (int c = 0; c < HD / 4; ++c) {
-                float4 q4[2], g4[2], k4[4], v4[4];
+                float4 q4[4], g4[4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    q4[i] = *reinterpret_cast<const float4*>(Qs + (ty * 2 + i) * QS + c * 4);
-                    g4[i] = *reinterpret_cast<const float4*>(Gs + (ty * 2 + i) * QS + c * 4);
+                for (int i = 0; i < 4; ++i) {
+                    q4[i] = *reinterpret_cast<const float4*>(Qs + (ty * 4 + i) * QS + c * 4);
+                    g4[i] = *reinterpret_cast<const float4*>(Gs + (ty * 4 + i) * QS + c * 4);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    k4[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
-                    v4[j] = *reinterpret_cast<const float4*>(Vs + (tx + 16 * j) * QS + c * 4);
-                }
+                    const float4 k4 = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
+                    const float4 v4 = *reinterpret_cast<const float4*>(Vs + (tx + 16 * j) * QS + c * 4);
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        s[i][j] = fmaf(q4[i].x, k4[j].x, s[i][j]); s[i][j] = fmaf(q4[i].y, k4[j].y, s[i][j]);
-                        s[i][j] = fmaf(q4[i].z, k4[j].z, s[i][j]); s[i][j] = fmaf(q4[i].w, k4[j].w, s[i][j]);
-                        dp[i][j] = fmaf(g4[i].x, v4[j].x, dp[i][j]); dp[i][j] = fmaf(g4[i].y, v4[j].y, dp[i][j]);
-                        dp[i][j] = fmaf(g4[i].z, v4[j].z, dp[i][j]); dp[i][j] = fmaf(g4[i].w, v4[j].w, dp[i][j]);
+                    for (int i = 0; i < 4; ++i) {
+                        s[i][j] = fmaf(q4[i].x, k4.x, s[i][j]); s[i][j] = fmaf(q4[i].y, k4.y, s[i][j]);
+                        s[i][j] = fmaf(q4[i].z, k4.z, s[i][j]); s[i][j] = fmaf(q4[i].w, k4.w, s[i][j]);
+                        dp[i][j] = fmaf(g4[i].x, v4.x, dp[i][j]); dp[i][j] = fmaf(g4[i].y, v4.y, dp[i][j]);
+                        dp[i][j] = fmaf(g4[i].z, v4.z, dp[i][j]); dp[i][j] = fmaf(g4[i].w, v4.w, dp[i][j]);
                     }
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int key = k0 + tx + 16 * j, r = ty * 2 + i;
+                    const int key = k0 + tx + 16 * j, r = ty * 4 + i;
                     const float p = key < len ? expf(s[i][j] * scale - s_lse[r]) : 0.f;
                     const float mk = attn_keep(seed, drop_p, inv_keep, b, h, q0 + r, key, H, L);
                     Ps[r * PS + tx + 16 * j] = p * mk;
@@ -308,7 +307,7 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
     FS2K_CHECK_LAUNCH();
     const int QS = head_dim + 4;
     const int smem_dq = ((64 + 64 + 32 + 32) * QS + 64 * 36) * 4;
-    const int smem_dkv = ((64 + 64 + 32 + 32) * QS + 2 * 32 * 68) * 4;
+    const int smem_dkv = ((64 + 64 + 64 + 64) * QS + 2 * 64 * 68) * 4;
     cudaError_t e;
     if (head_dim == 128) {
         e = cudaFuncSetAttribute(attn_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
