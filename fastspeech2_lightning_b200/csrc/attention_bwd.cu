@@ -40,7 +40,7 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, 
                    float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    constexpr int BQ = 64, BKEY = 32, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
+    constexpr int BQ = 64, BKEY = 64, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;               // [BQ][QS]
     float* Gs = Qs + BQ * QS;       // dO [BQ][QS]
@@ -91,36 +91,37 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, 
             *reinterpret_cast<float4*>(Vs + r * QS + c * 4) = vv;
         }
         __syncthreads();
-        float s[4][2], dp[4][2];
+        // 4 queries × 4 keys per thread (24 shared-memory wavefronts per 128 FFMA; 4×2 over 32-key tiles was LDS-bound)
+        float s[4][4], dp[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = dp[i][0] = dp[i][1] = 0.f;
-#pragma unroll 4
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+#pragma unroll 2
         for (int c = 0; c < HD / 4; ++c) {
-            float4 q4[4], g4[4], k4[2], v4[2];
+            float4 q4[4], g4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 q4[i] = *reinterpret_cast<const float4*>(Qs + (ty * 4 + i) * QS + c * 4);
                 g4[i] = *reinterpret_cast<const float4*>(Gs + (ty * 4 + i) * QS + c * 4);
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                k4[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
-                v4[j] = *reinterpret_cast<const float4*>(Vs + (tx + 16 * j) * QS + c * 4);
-            }
+            for (int j = 0; j < 4; ++j) {
+                const float4 k4 = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
+                const float4 v4 = *reinterpret_cast<const float4*>(Vs + (tx + 16 * j) * QS + c * 4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    s[i][j] = fmaf(q4[i].x, k4[j].x, s[i][j]); s[i][j] = fmaf(q4[i].y, k4[j].y, s[i][j]);
-                    s[i][j] = fmaf(q4[i].z, k4[j].z, s[i][j]); s[i][j] = fmaf(q4[i].w, k4[j].w, s[i][j]);
-                    dp[i][j] = fmaf(g4[i].x, v4[j].x, dp[i][j]); dp[i][j] = fmaf(g4[i].y, v4[j].y, dp[i][j]);
-                    dp[i][j] = fmaf(g4[i].z, v4[j].z, dp[i][j]); dp[i][j] = fmaf(g4[i].w, v4[j].w, dp[i][j]);
+                for (int i = 0; i < 4; ++i) {
+                    s[i][j] = fmaf(q4[i].x, k4.x, s[i][j]); s[i][j] = fmaf(q4[i].y, k4.y, s[i][j]);
+                    s[i][j] = fmaf(q4[i].z, k4.z, s[i][j]); s[i][j] = fmaf(q4[i].w, k4.w, s[i][j]);
+                    dp[i][j] = fmaf(g4[i].x, v4.x, dp[i][j]); dp[i][j] = fmaf(g4[i].y, v4.y, dp[i][j]);
+                    dp[i][j] = fmaf(g4[i].z, v4.z, dp[i][j]); dp[i][j] = fmaf(g4[i].w, v4.w, dp[i][j]);
                 }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 const int key = k0 + tx + 16 * j;
                 const float p = key < len ? expf(s[i][j] * scale - lse_r[i]) : 0.f;
                 const float mk = attn_keep(seed, drop_p, inv_keep, b, h, q0 + ty * 4 + i, key, H, L);
@@ -306,7 +307,7 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
     fs2k_launch(attn_delta_kernel, dim3((int)g), dim3(256), 0, s, out, dout, B, L, H, head_dim, delta);
     FS2K_CHECK_LAUNCH();
     const int QS = head_dim + 4;
-    const int smem_dq = ((64 + 64 + 32 + 32) * QS + 64 * 36) * 4;
+    const int smem_dq = ((64 + 64 + 64 + 64) * QS + 64 * 68) * 4;
     const int smem_dkv = ((64 + 64 + 64 + 64) * QS + 2 * 64 * 68) * 4;
     cudaError_t e;
     if (head_dim == 128) {
