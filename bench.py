@@ -54,9 +54,9 @@ def peaks():
 
 def ncu_traffic(workload: str, entry_point: str):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel behind `entry_point`, from the
-    committed ncu pass of the same workload (profiles/r1_summary_<workload>_v3.json, made by profiles/summarize_launches.py
+    committed ncu pass of the same workload (profiles/r1_summary_<workload>_v4.json, made by profiles/summarize_launches.py
     from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`); None when there is none."""
-    f = ROOT / "profiles" / f"r1_summary_{workload}_v3.json"
+    f = ROOT / "profiles" / f"r1_summary_{workload}_v4.json"
     names = {"fs2k_gemm_tc": "gemm_tc_kernel", "fs2k_mas_fwd": "mas_dp_kernel", "fs2k_attention_f32": "attention_simt_kernel"}
     if not f.exists() or entry_point not in names:
         return None
