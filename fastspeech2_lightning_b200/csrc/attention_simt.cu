@@ -13,7 +13,7 @@
 
 namespace fs2k {
 
-constexpr int ABQ = 64, ABK = 64;
+constexpr int ABQ = 64, ABK = 32;
 
 template <int HD>
 __global__ void __launch_bounds__(256)
@@ -66,35 +66,33 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
             *reinterpret_cast<float4*>(Vs + r * HD + c * 4) = vv;
         }
         __syncthreads();
-        // S = Q Kᵀ (4 queries × 4 keys per thread: 20 shared-memory wavefronts per 64 FFMA; 4×2 over 32-key tiles needed 16 per 32)
-        float s[4][4];
+        // S = Q Kᵀ (4 queries × 2 keys per thread)
+        float s[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-#pragma unroll 4
+        for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
+#pragma unroll 8
         for (int c = 0; c < HD / 4; ++c) {
-            float4 q4[4];
+            float4 q4[4], k4[2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) q4[i] = *reinterpret_cast<const float4*>(Qs + (ty * 4 + i) * QS + c * 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 k4 = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
+            for (int j = 0; j < 2; ++j) k4[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + c * 4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    s[i][j] = fmaf(q4[i].x, k4.x, s[i][j]);
-                    s[i][j] = fmaf(q4[i].y, k4.y, s[i][j]);
-                    s[i][j] = fmaf(q4[i].z, k4.z, s[i][j]);
-                    s[i][j] = fmaf(q4[i].w, k4.w, s[i][j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    s[i][j] = fmaf(q4[i].x, k4[j].x, s[i][j]);
+                    s[i][j] = fmaf(q4[i].y, k4[j].y, s[i][j]);
+                    s[i][j] = fmaf(q4[i].z, k4[j].z, s[i][j]);
+                    s[i][j] = fmaf(q4[i].w, k4[j].w, s[i][j]);
                 }
-            }
         }
         // online softmax
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const int key = k0 + tx + 16 * j;
                 s[i][j] = key < len ? s[i][j] * scale : -INFINITY;
                 mx = fmaxf(mx, s[i][j]);
@@ -106,7 +104,7 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
             const float corr = expf(m_run[i] - m_use);
             float rs = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const float p = expf(s[i][j] - m_use);
                 rs += p;  // the softmax normaliser uses the un-dropped probabilities
                 Ps[(ty * 4 + i) * PS + tx + 16 * j] =
@@ -185,10 +183,6 @@ extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int 
         fs2k_launch(attention_simt_kernel<128>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     } else {
         const int smem = (ABQ * 68 + ABK * 68 + ABK * 64 + ABQ * (ABK + 4)) * 4;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        }
         fs2k_launch(attention_simt_kernel<64>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
     }
     FS2K_CHECK_LAUNCH();
