@@ -456,8 +456,6 @@ def cpu_train_baseline(wl, steps=1):
 
 
 def run_mas(args, wl_name, wl, rank, world, device, pk):
-    import numpy as np
-
     from fastspeech2_lightning_b200 import ops
 
     B, F, T = wl["batch"], wl["F"], wl["T"]

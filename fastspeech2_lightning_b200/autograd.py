@@ -4,7 +4,6 @@ libfs2k kernels (see autograd_fns.py).  Without grad mode these are plain kernel
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 

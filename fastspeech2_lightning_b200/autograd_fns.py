@@ -3,7 +3,6 @@ torch.autograd only sequences them.  `autograd.py` routes here whenever a gradie
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 from torch.autograd.function import once_differentiable

@@ -1,6 +1,5 @@
 """FastSpeech2Loss — mirror of reference fs2/loss.py:9-126: same keys, weights and reductions
 (means over the whole padded tensors after masking both operands)."""
-import torch
 from torch import nn
 
 from .. import autograd_fns as fns

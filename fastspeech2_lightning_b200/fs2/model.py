@@ -15,7 +15,6 @@ from torch import nn
 
 from .. import autograd as ag
 from .. import autograd_fns as fns
-from .. import functional as Fk
 from .. import ops
 from .._lib import require_device
 from .config import N_PHONOLOGICAL_FEATURES, FastSpeech2Config, TargetTrainingTextRepresentationLevel

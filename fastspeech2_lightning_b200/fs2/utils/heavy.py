@@ -1,7 +1,6 @@
 """mask_from_lens — mirror of reference fs2/utils/heavy.py:11-15 (plotting helpers are out of scope)."""
 from typing import Optional
 
-import torch
 
 from ... import ops
 

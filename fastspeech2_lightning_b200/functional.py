@@ -6,12 +6,10 @@ are to the reference files (under /root/reference) or torchaudio's `models/confo
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 
 from . import autograd as ag
-from . import ops
 
 
 # ---------------------------------------------------------------------------------------------
