@@ -188,7 +188,7 @@ extern "C" int fs2k_act_bwd(const float* g, const float* aux, int mode, float al
 extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, int accumulate, fs2k_stream_t stream) {
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
-    FS2K_REQUIRE(z && out, FS2K_ERR_NULL);
+    FS2K_REQUIRE(out && (z || M == 0), FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * C, s);

@@ -209,7 +209,7 @@ extern "C" int fs2k_colstats(const float* z, long M, int C, double* sums /* [2*C
                              fs2k_stream_t stream) {
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
-    FS2K_REQUIRE(z && sums, FS2K_ERR_NULL);
+    FS2K_REQUIRE(sums && (z || M == 0), FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);

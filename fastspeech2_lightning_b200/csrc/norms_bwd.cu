@@ -206,7 +206,7 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((D & 3) == 0 && D <= 1024, FS2K_ERR_UNSUPPORTED);
-    FS2K_REQUIRE(g && x && mean && rstd && gamma && dx && dgamma && dbeta, FS2K_ERR_NULL);
+    FS2K_REQUIRE(dgamma && dbeta && (M == 0 || (g && x && mean && rstd && gamma && dx)), FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
     if (!accumulate) {  // otherwise the atomics add on top of what dgamma / dbeta already hold
@@ -234,7 +234,7 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
-    FS2K_REQUIRE(g && z && scale && shift && mean && rstd && sums && gz, FS2K_ERR_NULL);
+    FS2K_REQUIRE(sums && (M == 0 || (g && z && scale && shift && mean && rstd && gz)), FS2K_ERR_NULL);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);

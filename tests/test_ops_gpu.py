@@ -417,3 +417,32 @@ def test_gemm_tensor_core(mode, tol, B, L, K, N, taps, act, extra):
         close(got[1], ln_ref, tol * 5, what + " ln")
         if ln2_ref is not None:
             close(got[2], ln2_ref, tol * 5, what + " ln2")
+
+
+def test_zero_sized_calls_are_no_ops():
+    """Empty batches / zero rows must return empty results without touching the GPU state (every C entry point returns
+    FS2K_OK before its null checks when there is nothing to do)."""
+    from fastspeech2_lightning_b200 import ops
+
+    dev = "cuda:0"
+    w = torch.randn(256, 256, device=dev)
+    b = torch.randn(256, device=dev)
+    assert ops.gemm(torch.empty(0, 256, device=dev), w, b).shape == (0, 256)
+    assert ops.gemm(torch.empty(0, 17, 256, device=dev), w, b, residual=torch.empty(0, 17, 256, device=dev)).shape == (0, 17, 256)
+    assert ops.layernorm(torch.empty(0, 256, device=dev), b, b, 1e-5).shape == (0, 256)
+    qkv = torch.empty(0, 9, 768, device=dev)
+    assert ops.attention(qkv, torch.empty(0, dtype=torch.int32, device=dev), 2).shape == (0, 9, 256)
+    path, dur, hard = ops.mas(torch.empty(0, 1, 12, 5, device=dev), torch.empty(0, dtype=torch.int32, device=dev),
+                              torch.empty(0, dtype=torch.int32, device=dev))
+    assert hard.shape == (0, 1, 12, 5) and dur.shape == (0, 5)
+    cum, total = ops.lr_scan(torch.empty(0, 7, dtype=torch.int32, device=dev))
+    assert cum.shape == (0, 7) and total.shape == (0,)
+    assert ops.colsum(torch.empty(0, 256, device=dev)).abs().sum() == 0
+    e = torch.empty(0, 256, device=dev)
+    dx, dg, db = ops.layernorm_bwd(e, e, torch.empty(0, device=dev), torch.empty(0, device=dev), b)
+    assert dx.shape == (0, 256) and float(dg.abs().sum()) == 0 and float(db.abs().sum()) == 0
+    # an utterance of zero phones / zero frames inside a batch: durations all zero → nothing expanded, mask all False
+    dur = torch.tensor([[2, 1, 0], [0, 0, 0]], dtype=torch.int32, device=dev)
+    cum, total = ops.lr_scan(dur)
+    assert total.tolist() == [3, 0]
+    torch.cuda.synchronize()
