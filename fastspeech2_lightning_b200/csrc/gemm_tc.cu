@@ -5,7 +5,7 @@
 //                 + residual[(b,l), n]) · row_mask[(b,l)]          (+ optional LayerNorm of the finished row)
 //
 // One 128 × BLOCK_N output tile per CTA (BLOCK_N = N when N ≤ 256, else 256).  Operands stay fp32 in
-// HBM: TMA brings 128-row × 32-float boxes (one 128-byte swizzle atom per row) into a 4-stage ring; the
+// HBM: TMA brings 128-row × 32-float boxes (one 128-byte swizzle atom per row) into a ring of 2 (3×TF32) to 4 stages; the
 // convolution taps are time-shifted boxes of a 3-D tensor map [B][L][K] whose out-of-range rows TMA
 // zero-fills, so a tap never crosses an utterance boundary and no im2col buffer exists.  One elected
 // thread issues four K=8 tf32 MMAs per stage.  `passes = 3` adds the split-accumulate 3×TF32 scheme
@@ -15,7 +15,8 @@
 // during the main loop (3×TF32 only), then TMEM → registers → raw staging tile in shared memory; finally
 // all twelve warps run the store pass: per-column math (bias, folded BatchNorm, activation, alpha),
 // residual, row mask and, when requested, the LayerNorm of the row (a row lives in one warp, so mean and
-// variance are two shuffle reductions), with fully coalesced 16-byte global accesses, four rows in flight.
+// variance are two shuffle reductions), with fully coalesced 16-byte global accesses.  Dropout and the LayerNorm tail are
+// template flags: anything living in the store loop costs every launch.
 #include "tc_common.cuh"
 
 namespace fs2k {
