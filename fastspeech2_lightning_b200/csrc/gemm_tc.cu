@@ -106,7 +106,7 @@ template <bool LNORM> struct TcRowsPerIter { static constexpr int value = 1; }; 
 template <int PASSES, bool DROPOUT, bool LNORM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
+               const __grid_constant__ CUtensorMap tmBs, int presplit_b, int L, long M_total, int K, int N, int block_n, int taps, int pad, int tiles_per_b, int n_stages,
                TcEpilogue ep) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
@@ -156,9 +156,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tap = it / nk, k0 = (it - tap * nk) * TC_BK;
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
                 const uint32_t bar = smem_u32(&s_full[s]);
-                mbar_expect_tx(bar, a_bytes + b_bytes);
+                // presplit_b (3×TF32): the weights' small parts were computed once per weight version in global memory;
+                // TMA brings them straight into the small slot and the splitter warps only handle the A tile
+                const bool pre = PASSES == 3 && presplit_b;
+                mbar_expect_tx(bar, a_bytes + b_bytes + (pre ? b_bytes : 0u));
                 tma_load_3d(sa, &tmA, bar, k0, l0 + tap - pad, b_idx);
                 tma_load_2d(sb, &tmB, bar, k0, tap * N + n0);
+                if (pre) tma_load_2d(sb + a_bytes + b_bytes, &tmBs, bar, k0, tap * N + n0);
             }
         }
     } else if (warp == 1) {
@@ -196,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(smem_u32(&s_full[s]), ph);
                 const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
                 float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes + b_bytes);
-                split_small(src, dst, (a_bytes + b_bytes) / 16, et, TC_EPI_WARPS * 32);
+                split_small(src, dst, (presplit_b ? a_bytes : a_bytes + b_bytes) / 16, et, TC_EPI_WARPS * 32);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes → visible to the MMA proxy
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_split[s])) : "memory");
             }
@@ -357,7 +361,7 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
                             const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
                             const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
                             const float* ln2_gamma, const float* ln2_beta, float* ln2_out, float dropout_p, long seed,
-                            int passes, fs2k_stream_t stream) {
+                            int passes, const float* W_small, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && K > 0 && N > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(act >= 0 && act <= 3 && (passes == 1 || passes == 3), FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FS2K_ERR_BAD_SHAPE);
@@ -390,7 +394,8 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
 
     const int bk = passes == 3 ? TcBK<3>::value : TcBK<1>::value;
     const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBs;
+    const int presplit_b = (passes == 3 && W_small != nullptr) ? 1 : 0;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Lm, (cuuint64_t)Bm};
         cuuint64_t strides[2] = {(cuuint64_t)lda * 4, (cuuint64_t)Lm * lda * 4};
@@ -407,6 +412,10 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
+        r = encode(&tmBs, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(presplit_b ? W_small : W), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
@@ -430,7 +439,7 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        fs2k_launch(kernel, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
+        fs2k_launch(kernel, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmB, tmBs, presplit_b, (int)Lm, M, K, N, block_n, taps, pad, tiles_per_b, n_stages, ep);
         return cudaSuccess;
     };
     const bool drop = dropout_p > 0.f;
@@ -439,6 +448,27 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
     else if (passes == 3) e = drop ? launch(gemm_tc_kernel<3, true, false>) : launch(gemm_tc_kernel<3, false, false>);
     else e = drop ? launch(gemm_tc_kernel<1, true, false>) : launch(gemm_tc_kernel<1, false, false>);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+namespace fs2k {
+__global__ void __launch_bounds__(256) split_small_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+    pdl_prologue();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        out[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    }
+}
+}  // namespace fs2k
+
+extern "C" int fs2k_split_small(const float* x, long n, float* out, fs2k_stream_t stream) {
+    FS2K_REQUIRE(n >= 0, FS2K_ERR_BAD_SHAPE);
+    if (n == 0) return FS2K_OK;
+    FS2K_REQUIRE(x && out, FS2K_ERR_NULL);
+    long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    fs2k_launch(fs2k::split_small_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, x, n, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -339,14 +339,14 @@ class backward_precision:
 
 def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None, alpha: float = 1.0,
          residual=None, row_mask=None, out=None, ln=None, ln2=None, want_c: bool = True, dropout_p: float = 0.0,
-         seed: int = 0):
+         seed: int = 0, w_small=None):
     """a [B,L,K] (or [M,K]) · w [taps,N,K] or [N,K] with the fused epilogue of fs2k_gemm_{tc,f32}.
 
     ln = (gamma, beta, eps): also return LayerNorm(result) — fused into the tensor-core epilogue when one
     tile spans the row, otherwise a separate fs2k_layernorm_fwd launch; ln2 = (gamma, beta) chains a second
     LayerNorm on the first one's output.  Returns C, or (C, ln_out[, ln2_out]) when ln is given."""
     if ln is not None or PRECISION != "fp32":
-        r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p, seed)
+        r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p, seed, w_small)
         if r is not None:
             return r
     if dropout_p:  # SIMT fallback: dropout(+residual) as its own launch
@@ -363,7 +363,19 @@ def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None
     return c, y, layernorm(y, ln2[0], ln2[1], ln[2])
 
 
-def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p=0.0, seed=0):
+def split_small(x):
+    """x − tf32(x): the small operand of the 3×TF32 scheme.  `gemm(..., w_small=split_small(w))` lets the kernel load the
+    weights' small parts with TMA instead of splitting the weight tile in shared memory at every k-block: 17.6 → 16.3 µs
+    per GEMM in a back-to-back chain, but < 1 % on the full training / synthesis steps (measured), so the model code does
+    not carry the per-weight caches it would need; the capability stays for callers with static weights."""
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    check(lib().fs2k_split_small(_p(x), x.numel(), _p(out), _stream()), "fs2k_split_small")
+    _count()
+    return out
+
+
+def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p=0.0, seed=0, w_small=None):
     if PRECISION == "fp32":
         return None
     a = _f32(a, "a")
@@ -393,7 +405,8 @@ def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask,
                              float(alpha), _p(residual), N, _p(row_mask), _p(c), N,
                              _p(ln[0]) if fuse_ln else None, _p(ln[1]) if fuse_ln else None, float(ln[2]) if fuse_ln else 0.0,
                              _p(ln_out), _p(ln2[0]) if ln2_out is not None else None, _p(ln2[1]) if ln2_out is not None else None,
-                             _p(ln2_out), float(dropout_p), int(seed), 3 if PRECISION == "tf32x3" else 1, _stream()), "fs2k_gemm_tc")
+                             _p(ln2_out), float(dropout_p), int(seed), 3 if PRECISION == "tf32x3" else 1,
+                             _p(w_small) if (w_small is not None and PRECISION == "tf32x3") else None, _stream()), "fs2k_gemm_tc")
     _count()
     if ln is None:
         return c

@@ -130,6 +130,8 @@ int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const float* W, 
  * ln_out = LN(C; ln_gamma, ln_beta), ln2_out = LN(ln_out; ln2_gamma, ln2_beta); C may be NULL if only
  * the normalised row is wanted.  dropout_p > 0: the value is dropped (counter hash of (seed, m*N + n), scaled by
  * 1/(1-p)) before the residual is added — `residual + Dropout(Linear(x))*alpha` in one launch.
+ * W_small (optional, passes = 3): x - tf32(x) of every weight, same layout as W (fs2k_split_small) — the kernel then loads
+ * it with TMA instead of splitting the weight tile in shared memory at every k-block.
  * fs2k_gemm_tc_supported: K % 4 == 0, lda % 4 == 0, N % 16 == 0 (N <= 256)
  * or N % 128 == 0. */
 int fs2k_gemm_tc_supported(int K, int N, int lda, int taps);
@@ -139,7 +141,9 @@ int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, i
                  const float* bias, const float* scale, const float* shift, int act, float alpha,
                  const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, const float* ln_gamma,
                  const float* ln_beta, float ln_eps, float* ln_out, const float* ln2_gamma, const float* ln2_beta,
-                 float* ln2_out, float dropout_p, long seed, int passes, fs2k_stream_t stream);
+                 float* ln2_out, float dropout_p, long seed, int passes, const float* W_small, fs2k_stream_t stream);
+/* out[i] = x[i] - tf32_truncate(x[i]): the "small" operand of the 3xTF32 scheme */
+int fs2k_split_small(const float* x, long n, float* out, fs2k_stream_t stream);
 int fs2k_rowdot(const float* x, const float* w, const float* b, const uint8_t* mask, long M, int D, float* y,
                 fs2k_stream_t stream);
 int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, float* out, fs2k_stream_t stream);

@@ -57,3 +57,27 @@ for pdl in (1, 0):
     for _ in range(10): g.replay()
     e.record(); torch.cuda.synchronize()
     print("graph memset+colsum x100 pdl", pdl, "us per pair", s.elapsed_time(e) * 1000 / 1000)
+
+# weights pre-split in global memory vs split in shared memory at every k-block
+_lib.lib().fs2k_set_pdl(1)
+ws = ops.split_small(w)
+def chain_gemm_pre():
+    y = big
+    for _ in range(50):
+        y = ops.gemm(y, w, None, residual=big, w_small=ws)
+    return y
+ref = ops.gemm(big, w, None, residual=big)
+got = ops.gemm(big, w, None, residual=big, w_small=ws)
+print("presplit max |diff| vs in-kernel split:", float((ref - got).abs().max()))
+for name, fn in (("gemm x50 in-kernel split", chain_gemm), ("gemm x50 presplit W", chain_gemm_pre)) * 2:
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3): g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20): g.replay()
+    e.record(); torch.cuda.synchronize()
+    print(name, "us per gemm", s.elapsed_time(e) / 20 / 50 * 1000)

@@ -240,3 +240,21 @@ def test_reduced_precision_decoder_mode_meets_the_mel_l1_bar():
             print(f"{name}: decoder in single-pass TF32, mel L1 of {k} = {l1:.2e} (mean |mel| {float(ref.abs().mean()):.2f})")
             assert l1 <= 1e-2, (name, k, l1)
             assert l1 > 1e-7  # the mode is really active
+
+
+def test_synthesis_graphs_follow_in_place_weight_changes():
+    """Captured synthesis graphs bake in tensors derived from the weights (pre-split small operands): after an in-place
+    weight change the next predict_step must re-capture and agree with the eager forward of the changed model."""
+    meta, _ = load_case("infer_tf")
+    model = build_model(meta).eval()
+    batch = case_batch(meta, DEV)
+    model.enable_cuda_graphs()
+    before = model.predict_step(batch, 0)[model.output_key].clone()
+    model.predict_step(batch, 1)  # replay
+    with torch.no_grad():
+        model.mel_linear.weight.mul_(1.25)
+        model.decoder.conformer_layers[0].ffn1.sequential[1].weight.add_(0.01)
+        after = model.predict_step(batch, 2)[model.output_key].clone()
+        eager = model(batch, inference=True)[model.output_key]
+    assert float((after - before).abs().max()) > 1e-3
+    close(after, eager, 1e-5, "graph replay after weight change vs eager")

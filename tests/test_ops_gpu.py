@@ -446,3 +446,21 @@ def test_zero_sized_calls_are_no_ops():
     cum, total = ops.lr_scan(dur)
     assert total.tolist() == [3, 0]
     torch.cuda.synchronize()
+
+
+def test_gemm_with_presplit_weights_is_bit_identical():
+    """3×TF32 with the weights' small parts pre-computed in global memory (fs2k_split_small, loaded by TMA) must give
+    exactly what the in-kernel split gives — same operands, same MMA order."""
+    from fastspeech2_lightning_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    for (B, L, K, N) in [(3, 130, 256, 256), (2, 77, 256, 1024), (4, 64, 1024, 256), (1, 40, 64, 80)]:
+        x = torch.randn(B, L, K, generator=g).to("cuda:0")
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to("cuda:0")
+        b = torch.randn(N, generator=g).to("cuda:0")
+        ws = ops.split_small(w)
+        big = w.view(torch.int32).bitwise_and(-8192).view(torch.float32)  # 0xFFFFE000
+        assert torch.equal(ws, w - big)
+        a = ops.gemm(x, w, b, act="silu")
+        c = ops.gemm(x, w, b, act="silu", w_small=ws)
+        assert torch.equal(a, c), (B, L, K, N)
