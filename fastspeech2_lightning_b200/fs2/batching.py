@@ -132,9 +132,20 @@ def collate_to_device(data, device, learn_alignment: bool = True) -> dict:
     return out
 
 
-def trim_predictions(outputs: dict, output_key: str = "postnet_output") -> list[torch.Tensor]:
+_pinned = {}  # device index → reusable pinned result buffer (cudaHostAlloc per call would cost more than the copy)
+
+
+def _pinned_buffer(device, n: int) -> torch.Tensor:
+    buf = _pinned.get(device.index)
+    if buf is None or buf.numel() < n:
+        buf = _pinned[device.index] = torch.empty(max(n, 1 << 20), dtype=torch.float32).pin_memory()
+    return buf
+
+
+def trim_predictions(outputs: dict, output_key: str = "postnet_output", reuse_buffer: bool = False) -> list[torch.Tensor]:
     """`[data[:tgt_len].cpu().transpose(0, 1) for data in outputs[output_key]]` (prediction_writing_callback.py:255-262)
-    as one device launch + one device→host copy.  Returns CPU tensors [n_mels, T_b] (views of one pinned buffer)."""
+    as one device launch + one device→host copy.  Returns CPU tensors [n_mels, T_b] (views of one pinned buffer; with
+    `reuse_buffer` the buffer is shared between calls — consume the result before the next call, as the callback does)."""
     mel = outputs[output_key]
     lens = outputs["tgt_lens"]
     assert mel is not None and lens is not None
@@ -148,6 +159,6 @@ def trim_predictions(outputs: dict, output_key: str = "postnet_output") -> list[
     check(lib().fs2k_trim_transpose(mel.contiguous().data_ptr(), lens.to(torch.int32).contiguous().data_ptr(), dev_offs.data_ptr(), B, F, C,
                                     packed.data_ptr(), torch.cuda.current_stream(mel.device).cuda_stream), "fs2k_trim_transpose")
     ops._count()
-    host = torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
+    host = _pinned_buffer(mel.device, total)[: max(total, 1)] if reuse_buffer else torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
     host.copy_(packed, non_blocking=False)
     return [host[int(offs[b]): int(offs[b + 1])].view(C, int(lens_host[b])) for b in range(B)]
