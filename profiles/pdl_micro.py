@@ -1,5 +1,7 @@
+"""Micro-benchmarks behind DESIGN.md's launch / epilogue findings: kernel-to-kernel gap and GEMM chain inside a CUDA graph
+with and without programmatic dependent launch, eager launch cost, memset interaction, pre-split weights."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fastspeech2_lightning_b200 import ops, _lib
 x = torch.randn(1024, device="cuda")
 big = torch.randn(32, 500, 256, device="cuda")
