@@ -88,12 +88,12 @@ def dwconv(x, weight, bias):
     return ops.dwconv(x, weight, bias, channels=weight.shape[0])
 
 
-def attention(qkv, lengths, heads: int, dropout: float = 0.0):
+def attention(qkv, lengths, heads: int, dropout: float = 0.0, order=None):
     if _needs_grad(qkv) or dropout > 0.0:
         from . import autograd_fns as fns
 
-        return fns.attention(qkv, lengths, heads, dropout)
-    return ops.attention(qkv, lengths, heads)
+        return fns.attention(qkv, lengths, heads, dropout, order)
+    return ops.attention(qkv, lengths, heads, order=order)
 
 
 def rowdot(x, weight, bias, mask):

@@ -300,11 +300,12 @@ def dwconv(x, weight, bias):
 # ---------------------------------------------------------------------------------------------
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, lengths, heads, dropout_p):
+    def forward(ctx, qkv, lengths, heads, dropout_p, order):
         seed = int(torch.randint(0, 2**31 - 1, (1,)).item()) if dropout_p else 0
-        out, lse = ops.attention(qkv, lengths, heads, want_lse=True, dropout_p=dropout_p, seed=seed)
+        out, lse = ops.attention(qkv, lengths, heads, want_lse=True, dropout_p=dropout_p, seed=seed, order=order)
         ctx.save_for_backward(qkv, out, lse, lengths)
         ctx.meta = (heads, dropout_p, seed)
+        ctx.order = order
         return out
 
     @staticmethod
@@ -312,11 +313,11 @@ class _Attention(torch.autograd.Function):
     def backward(ctx, g):
         qkv, out, lse, lengths = ctx.saved_tensors
         heads, p, seed = ctx.meta
-        return ops.attention_bwd(qkv, out, lse, g.contiguous(), lengths, heads, p, seed), None, None, None
+        return ops.attention_bwd(qkv, out, lse, g.contiguous(), lengths, heads, p, seed, ctx.order), None, None, None, None
 
 
-def attention(qkv, lengths, heads, dropout_p=0.0):
-    return _Attention.apply(qkv.contiguous(), lengths, heads, float(dropout_p))
+def attention(qkv, lengths, heads, dropout_p=0.0, order=None):
+    return _Attention.apply(qkv.contiguous(), lengths, heads, float(dropout_p), order)
 
 
 class _Rowdot(torch.autograd.Function):

@@ -37,7 +37,7 @@ template <int HD>
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                    const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
-                   float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+                   float drop_p, unsigned long long seed, const int* __restrict__ order, float* __restrict__ dqkv) {
     pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int BQ = 64, BKEY = 64, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
@@ -47,7 +47,7 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, 
     float* Ks = Gs + BQ * QS;       // [BKEY][QS]
     float* Vs = Ks + BKEY * QS;     // [BKEY][QS]
     float* Ss = Vs + BKEY * QS;     // dS [BQ][PS]
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+    const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;  // longest utterance first
     const int D = H * HD, ld = 3 * D;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int len = min(lens[b], L);
@@ -162,7 +162,7 @@ template <int HD>
 __global__ void __launch_bounds__(256)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, const float* __restrict__ lse,
                     const float* __restrict__ delta, const int* __restrict__ lens, int L, int H, float scale,
-                    float drop_p, unsigned long long seed, float* __restrict__ dqkv) {
+                    float drop_p, unsigned long long seed, const int* __restrict__ order, float* __restrict__ dqkv) {
     pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int BKEY = 64, BQ = 64, QS = HD + 4, PS = BKEY + 4, NJ = HD / 64;
@@ -174,7 +174,7 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     float* Ps = Gs + BQ * QS;       // P  [BQ][PS]
     float* Ss = Ps + BQ * PS;       // dS [BQ][PS]
     __shared__ float s_lse[BQ], s_del[BQ];
-    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BKEY;
+    const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BKEY;  // longest utterance first
     const int D = H * HD, ld = 3 * D;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int len = min(lens[b], L);
@@ -294,7 +294,7 @@ using namespace fs2k;
 
 extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout,
                                       const int* lens, int B, int L, int H, int head_dim, float dropout_p, long seed,
-                                      float* delta /* [B,H,L] */, float* dqkv, fs2k_stream_t stream) {
+                                      float* delta /* [B,H,L] */, float* dqkv, const int* order, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && H > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(head_dim == 64 || head_dim == 128, FS2K_ERR_UNSUPPORTED);
     if (B == 0 || L == 0) return FS2K_OK;
@@ -314,16 +314,16 @@ extern "C" int fs2k_attention_bwd_f32(const float* qkv, const float* out, const 
         e = cudaFuncSetAttribute(attn_bwd_dq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(attn_bwd_dq_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dq_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, dqkv);
         FS2K_CHECK_LAUNCH();
-        fs2k_launch(attn_bwd_dkv_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dkv_kernel<128>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, dqkv);
     } else {
         e = cudaFuncSetAttribute(attn_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(attn_bwd_dq_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dq_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dq, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, dqkv);
         FS2K_CHECK_LAUNCH();
-        fs2k_launch(attn_bwd_dkv_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, dqkv);
+        fs2k_launch(attn_bwd_dkv_kernel<64>, dim3(dim3(cdiv(L, 64), H, B)), dim3(256), smem_dkv, s, qkv, dout, lse, delta, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, dqkv);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -18,7 +18,8 @@ constexpr int ABQ = 64, ABK = 32;
 template <int HD>
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ lens, int L, int H, float scale,
-                      float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ lse_out) {
+                      float drop_p, unsigned long long seed, const int* __restrict__ order, float* __restrict__ out,
+                      float* __restrict__ lse_out) {
     pdl_prologue();
     seed = seed_with_base(seed);
     constexpr int QS = HD + 4, PS = ABK + 4, NJ = HD / 64;
@@ -27,7 +28,9 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
     float* Ks = Qs + ABQ * QS;        // [ABK][QS]
     float* Vs = Ks + ABK * QS;        // [ABK][HD]
     float* Ps = Vs + ABK * HD;        // [ABQ][PS]
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ABQ;
+    // CTAs are dispatched in block-index order: `order` lists the utterances longest first (work ∝ lens[b]), so the
+    // short ones fill the tail of the last wave instead of leaving SMs idle behind a long one
+    const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ABQ;
     const int D = H * HD, ld = 3 * D;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int len = min(lens[b], L);
@@ -158,12 +161,36 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ len
     }
 }
 
+// order[rank] = utterance index, ranks by descending length (ties: lower index first).  One thread per utterance, O(B²).
+__global__ void attn_order_kernel(const int* __restrict__ lens, int B, int* __restrict__ order) {
+    pdl_prologue();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        const int li = lens[i];
+        int rank = 0;
+        for (int j = 0; j < B; ++j) {
+            const int lj = lens[j];
+            rank += (lj > li) || (lj == li && j < i);
+        }
+        order[rank] = i;
+    }
+}
+
 }  // namespace fs2k
 
 using namespace fs2k;
 
+// fills order_ws[B] (longest utterance first) for the attention kernels; B ≤ 4096
+extern "C" int fs2k_attention_order(const int* lens, int B, int* order_ws, fs2k_stream_t stream) {
+    FS2K_REQUIRE(B >= 0 && B <= 4096, FS2K_ERR_BAD_SHAPE);
+    if (B == 0) return FS2K_OK;
+    FS2K_REQUIRE(lens && order_ws, FS2K_ERR_NULL);
+    fs2k_launch(attn_order_kernel, dim3(cdiv(B, 128)), dim3(128), 0, (cudaStream_t)stream, lens, B, order_ws);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
 extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
-                                  long seed, float* out, float* lse_out, fs2k_stream_t stream) {
+                                  long seed, float* out, float* lse_out, const int* order, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && H > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(head_dim == 64 || head_dim == 128, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FS2K_ERR_BAD_SHAPE);
@@ -180,10 +207,10 @@ extern "C" int fs2k_attention_f32(const float* qkv, const int* lens, int B, int 
             if (e != cudaSuccess) return fs2k_set_cuda_error(e);
             set = true;
         }
-        fs2k_launch(attention_simt_kernel<128>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
+        fs2k_launch(attention_simt_kernel<128>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, out, lse_out);
     } else {
         const int smem = (ABQ * 68 + ABK * 68 + ABK * 64 + ABQ * (ABK + 4)) * 4;
-        fs2k_launch(attention_simt_kernel<64>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, out, lse_out);
+        fs2k_launch(attention_simt_kernel<64>, dim3(grid), dim3(256), smem, s, qkv, lens, L, H, scale, dropout_p, (unsigned long long)seed, order, out, lse_out);
     }
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -23,14 +23,14 @@ def _ffn_half(x, ffn, training: bool, p_drop: float):
     return ag.linear(h, s[4].weight, s[4].bias, alpha=0.5, residual=x, dropout=p_drop if training else 0.0)
 
 
-def conformer_layer(x, lengths, layer, training: bool):
+def conformer_layer(x, lengths, layer, training: bool, order=None):
     p = layer.dropout_p
     x = _ffn_half(x, layer.ffn1, training, p)
     # self-attention block (:191-203)
     ln = ag.layernorm(x, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, layer.self_attn_layer_norm.eps)
     mha = layer.self_attn
     qkv = ag.linear(ln, mha.in_proj_weight, mha.in_proj_bias)
-    o = ag.attention(qkv, lengths, layer.num_heads, dropout=mha.dropout if training else 0.0)
+    o = ag.attention(qkv, lengths, layer.num_heads, dropout=mha.dropout if training else 0.0, order=order)
     x = ag.linear(o, mha.out_proj.weight, mha.out_proj.bias, residual=x, dropout=p if training else 0.0)
     # convolution module (:42-75, :168-174)
     cm = layer.conv_module
@@ -46,8 +46,11 @@ def conformer_layer(x, lengths, layer, training: bool):
 
 def conformer_stack(x, lengths, conformer, training: bool):
     lengths = lengths.to(torch.int32)
+    from . import ops
+
+    order = ops.attention_order(lengths)  # once per stack: the attention CTAs of every layer run longest utterance first
     for layer in conformer.conformer_layers:
-        x = conformer_layer(x, lengths, layer, training)
+        x = conformer_layer(x, lengths, layer, training, order)
     return x
 
 

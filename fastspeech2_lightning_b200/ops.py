@@ -455,13 +455,25 @@ def rowdot(x, w, b=None, mask=None):
     return y
 
 
-def attention(qkv, lens, heads: int, want_lse: bool = False, dropout_p: float = 0.0, seed: int = 0):
+def attention_order(lens):
+    """Utterance indices, longest first (int32 [B]) — dispatch order of the attention CTAs (work ∝ length)."""
+    lens = _i32(lens, "lens")
+    B = lens.numel()
+    if B < 2 or B > 4096:
+        return None
+    order = torch.empty((B,), dtype=torch.int32, device=lens.device)
+    check(lib().fs2k_attention_order(_p(lens), B, _p(order), _stream()), "fs2k_attention_order")
+    _count()
+    return order
+
+
+def attention(qkv, lens, heads: int, want_lse: bool = False, dropout_p: float = 0.0, seed: int = 0, order=None):
     qkv, lens = _f32(qkv, "qkv"), _i32(lens, "lens")
     B, L, D3 = qkv.shape
     D = D3 // 3
     out = torch.empty((B, L, D), dtype=torch.float32, device=qkv.device)
     lse = torch.empty((B, heads, L), dtype=torch.float32, device=qkv.device) if want_lse else None
-    check(lib().fs2k_attention_f32(_p(qkv), _p(lens), B, L, heads, D // heads, float(dropout_p), int(seed), _p(out), _p(lse), _stream()), "fs2k_attention_f32")
+    check(lib().fs2k_attention_f32(_p(qkv), _p(lens), B, L, heads, D // heads, float(dropout_p), int(seed), _p(out), _p(lse), _p(order), _stream()), "fs2k_attention_f32")
     _count()
     return (out, lse) if want_lse else out
 
@@ -750,13 +762,13 @@ def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: f
     return gz, dgamma, dbeta
 
 
-def attention_bwd(qkv, out, lse, dout, lens, heads: int, dropout_p: float = 0.0, seed: int = 0):
+def attention_bwd(qkv, out, lse, dout, lens, heads: int, dropout_p: float = 0.0, seed: int = 0, order=None):
     qkv, out, dout = _f32(qkv, "qkv"), _f32(out, "out"), _f32(dout, "dout")
     B, L, D3 = qkv.shape
     D = D3 // 3
     delta = torch.empty((B, heads, L), dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
-    check(lib().fs2k_attention_bwd_f32(_p(qkv), _p(out), _p(lse), _p(dout), _p(_i32(lens)), B, L, heads, D // heads, float(dropout_p), int(seed), _p(delta), _p(dqkv), _stream()), "fs2k_attention_bwd_f32")
+    check(lib().fs2k_attention_bwd_f32(_p(qkv), _p(out), _p(lse), _p(dout), _p(_i32(lens)), B, L, heads, D // heads, float(dropout_p), int(seed), _p(delta), _p(dqkv), _p(order), _stream()), "fs2k_attention_bwd_f32")
     _count(3)
     return dqkv
 

@@ -151,8 +151,11 @@ int fs2k_repack_conv_weight(const float* w, int N, int K, int taps, float* out, 
 /* ---- attention (torchaudio conformer.py:151-153,193-202) ------------------------------------------
  * qkv [B,L,3·H·hd] packed in_proj output; out [B,L,H·hd]; keys >= lens[b] masked; lse_out optional [B,H,L];
  * dropout_p > 0 (training): dropout on the attention probabilities, mask = counter hash of (seed, b, h, q, k). */
+/* order (optional): utterance indices, longest first (fs2k_attention_order fills it from lens) — the attention kernels
+ * then dispatch the long utterances first so the ragged tail of the last wave is filled by short ones. */
+int fs2k_attention_order(const int* lens, int B, int* order_ws, fs2k_stream_t stream);
 int fs2k_attention_f32(const float* qkv, const int* lens, int B, int L, int H, int head_dim, float dropout_p, long seed,
-                       float* out, float* lse_out, fs2k_stream_t stream);
+                       float* out, float* lse_out, const int* order, fs2k_stream_t stream);
 
 /* ---- depthwise conv (conformer.py:50-65 with GLU/BatchNorm/SiLU fused; fs2/blocks.py:8-15) ---------
  * x [B,L,ldx] (glu: value c, gate c+C); w [C][K]; scale/shift non-NULL: y = silu((conv+bias)*scale+shift). */
@@ -229,6 +232,7 @@ int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const fl
 /* attention backward (flash style, recomputes P from lse); delta: [B,H,L] scratch; dqkv [B,L,3·H·hd] */
 int fs2k_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, const int* lens,
                            int B, int L, int H, int head_dim, float dropout_p, long seed, float* delta, float* dqkv,
+                           const int* order,
                            fs2k_stream_t stream);
 /* depthwise conv backward (glu: x = (value, gate) and dx has the same 2C layout); dw/dbias zeroed here */
 int fs2k_dwconv_bwd(const float* gz, const float* x, int ldx, int B, int L, int C, const float* w, int K, int glu,

@@ -464,3 +464,20 @@ def test_gemm_with_presplit_weights_is_bit_identical():
         a = ops.gemm(x, w, b, act="silu")
         c = ops.gemm(x, w, b, act="silu", w_small=ws)
         assert torch.equal(a, c), (B, L, K, N)
+
+
+def test_attention_longest_first_dispatch_order_changes_nothing():
+    """`order` only permutes which CTA works on which utterance: forward and backward must be bit-identical."""
+    from fastspeech2_lightning_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    B, L, H, hd = 7, 150, 2, 128
+    qkv = (torch.randn(B, L, 3 * H * hd, generator=g) * 0.5).to("cuda:0")
+    lens = torch.tensor([150, 33, 97, 150, 1, 64, 120], dtype=torch.int32, device="cuda:0")
+    order = ops.attention_order(lens)
+    assert order.tolist() == [0, 3, 6, 2, 5, 1, 4]
+    o0, lse0 = ops.attention(qkv, lens, H, want_lse=True)
+    o1, lse1 = ops.attention(qkv, lens, H, want_lse=True, order=order)
+    assert torch.equal(o0, o1) and torch.equal(lse0, lse1)
+    go = torch.randn(B, L, H * hd, generator=g).to("cuda:0")
+    assert torch.equal(ops.attention_bwd(qkv, o0, lse0, go, lens, H), ops.attention_bwd(qkv, o0, lse0, go, lens, H, order=order))
