@@ -628,5 +628,104 @@ def ctc_forward_sum_prefetch(attn_logprob, key_lens, query_lens, blank_logprob=-
     attn_logprob._fs2k_ctc = (loss, sink.stream, float(blank_logprob), key_lens, query_lens)
 
 
+# ---------------------------------------------------------------------------------------------
+# GST reference encoder, training path (fs2/gst/model.py:103-257)
+# ---------------------------------------------------------------------------------------------
+class _Conv2dS2BnRelu(torch.autograd.Function):
+    """Conv2d(3×3, stride 2, pad 1, no bias) → BatchNorm2d → ReLU on channels-last x [B,H,W,Ci]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bn_w, bn_b, bn, training):
+        w = weight.detach().permute(2, 3, 1, 0).contiguous()  # [Co,Ci,3,3] → [3,3,Ci,Co]
+        z = ops.conv2d_s2_raw(x, w)
+        z2 = z.view(-1, z.shape[-1])
+        scale, shift, mean, rstd = ops.bn_scale_shift(bn, z2, training, save_stats=True)
+        y = ops.affine_act(z2, scale, shift, "relu").view_as(z)
+        ctx.save_for_backward(x, w, z, scale, shift, mean, rstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w, z, scale, shift, mean, rstd = ctx.saved_tensors
+        Co = z.shape[-1]
+        gz, dgamma, dbeta = ops.bn_act_bwd(g.contiguous().view(-1, Co), z.view(-1, Co), scale, shift, mean, rstd, "relu", ctx.training)
+        gz = gz.view_as(z)
+        dx = ops.conv2d_s2_dgrad(gz, w, x.shape) if ctx.needs_input_grad[0] else None
+        dw = ops.conv2d_s2_wgrad(x, gz).permute(3, 2, 0, 1).contiguous()
+        return dx, dw, dgamma, dbeta, None, None
+
+
+def conv2d_s2_bn_relu(x, conv, bn, training):
+    return _Conv2dS2BnRelu.apply(x.contiguous(), conv.weight, bn.weight, bn.bias, bn, training)
+
+
+class _GruLastHidden(torch.autograd.Function):
+    """Last hidden state of a one-layer batch_first GRU (h0 = 0) with back-propagation through time."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh):
+        B, T, I = x.shape
+        U = w_hh.shape[1]
+        x2 = x.reshape(B * T, I)
+        xp = ops.gemm(x2, w_ih.detach(), b_ih.detach())
+        h = torch.zeros((B, U), dtype=torch.float32, device=x.device)
+        hs, hps = [], []
+        for t in range(T):
+            hp = ops.gemm(h, w_hh.detach(), b_hh.detach())
+            hs.append(h)
+            hps.append(hp)
+            h = ops.gru_gate(xp, t, T, hp, h)
+        ctx.save_for_backward(x2, w_ih, w_hh, xp, torch.stack(hs), torch.stack(hps))
+        ctx.shape = (B, T, I, U)
+        return h
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dh):
+        x2, w_ih, w_hh, xp, hs, hps = ctx.saved_tensors
+        B, T, I, U = ctx.shape
+        dxp = torch.empty_like(xp)
+        dw_hh = torch.zeros_like(w_hh)
+        db_hh = torch.zeros((3 * U,), dtype=torch.float32, device=dh.device)
+        wt_hh = ops.weight_taps_transposed(w_hh.detach().reshape(1, 3 * U, U))  # [1, U, 3U]
+        dh = dh.contiguous()
+        for t in range(T - 1, -1, -1):
+            dhp, dh_prev = ops.gru_gate_bwd(xp, dxp, t, T, hps[t], hs[t], dh)
+            ops.gemm_wgrad(dhp, hs[t], 1, 0, False, accumulate_into=dw_hh)
+            ops.colsum(dhp, out=db_hh, accumulate=True)
+            dh = ops.gemm(dhp, wt_hh, None, residual=dh_prev)
+        dw_ih = ops.gemm_wgrad(dxp, x2, 1, 0, False)
+        db_ih = ops.colsum(dxp)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dxp, ops.weight_taps_transposed(w_ih.detach().reshape(1, 3 * U, I)), None).view(B, T, I)
+        return dx, dw_ih, dw_hh, db_ih, db_hh
+
+
+def gru_last_hidden(x, gru):
+    return _GruLastHidden.apply(x.contiguous(), gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0)
+
+
+class _GstTokenAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        ctx.save_for_backward(q, k, v)
+        ctx.heads = heads
+        return ops.gst_token_attention(q, k, v, heads)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        q, k, v = ctx.saved_tensors
+        dq, dk, dv = ops.gst_token_attention_bwd(q, k, v, g.contiguous(), ctx.heads)
+        return dq, dk, dv, None
+
+
+def gst_token_attention(q, k, v, heads):
+    return _GstTokenAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(), heads)
+
+
 def tanh_row(table, index):
     return ops.tanh(table.detach()[index: index + 1].contiguous())

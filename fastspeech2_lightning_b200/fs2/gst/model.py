@@ -4,10 +4,11 @@
 * `condition_on_gst_tokens` (reference-free synthesis, gst/model.py:77-85): a single key ⇒ the
   softmax is identically 1 ⇒ linear_out(linear_v(tanh(gst_embs[index]))), two libfs2k GEMMs.
 * `forward(speech)` (reference encoder: 6×Conv2d s2 + BatchNorm2d + ReLU → GRU → 4-head token
-  attention): synthesis / validation (eval mode, no gradient) runs on libfs2k
-  kernels (csrc/gst.cu: direct channels-last conv + folded BN + ReLU, GRU = tensor-core GEMMs + gate
-  kernel, token attention); training through it still uses torch autograd over cuDNN / ATen library
-  calls on the GPU (no CPU path), marked LIBRARY in DESIGN.md.
+  attention) runs on libfs2k kernels (csrc/gst.cu): synthesis / validation with
+  folded BatchNorm in one fused conv kernel; training through autograd Functions over the raw conv, the
+  BatchNorm batch-statistics kernels, conv dgrad / wgrad, a GRU with back-propagation through time and
+  the token-attention backward (`TRAINING_KERNELS = False` selects torch's cuDNN / ATen path instead,
+  which CPU tensors always take).
 """
 import math
 from collections.abc import Sequence
@@ -16,6 +17,11 @@ import torch
 
 from ... import autograd as ag
 from ... import ops
+
+
+# Training through the reference encoder / token layer on libfs2k kernels (autograd Functions over the conv / BatchNorm /
+# GRU / attention kernels).  False = torch autograd over cuDNN / ATen library calls.
+TRAINING_KERNELS = True
 
 
 def _kernel_path(module, *tensors) -> bool:
@@ -73,7 +79,7 @@ class ReferenceEncoder(torch.nn.Module):
         self.gru = torch.nn.GRU(gru_in_units, gru_units, gru_layers, batch_first=True)
 
     def forward(self, speech: torch.Tensor) -> torch.Tensor:
-        """gst/model.py:179-199.  Eval without gradients: libfs2k kernels; otherwise the LIBRARY path below."""
+        """gst/model.py:179-199.  CUDA inputs run on libfs2k kernels (fused eval path or autograd Functions)."""
         if _kernel_path(self, speech):
             x = speech.detach().contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
             n = len(self.convs) // 3
@@ -86,6 +92,15 @@ class ReferenceEncoder(torch.nn.Module):
             g = self.gru
             return ops.gru_last_hidden(hs, g.weight_ih_l0.detach(), g.weight_hh_l0.detach(), g.bias_ih_l0.detach(),
                                        g.bias_hh_l0.detach())
+        if TRAINING_KERNELS and speech.is_cuda:
+            from ... import autograd_fns as fns
+
+            x = speech.contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
+            n = len(self.convs) // 3
+            for i in range(n):
+                x = fns.conv2d_s2_bn_relu(x, self.convs[3 * i], self.convs[3 * i + 1], self.training)
+            hs = x.permute(0, 1, 3, 2).reshape(x.shape[0], x.shape[1], -1)  # [B,T',W',C] → [B,T',C·W'] (:195-197)
+            return fns.gru_last_hidden(hs, self.gru)
         batch_size = speech.size(0)
         hs = self.convs(speech.unsqueeze(1)).transpose(1, 2)
         hs = hs.contiguous().view(batch_size, hs.size(1), -1)
@@ -111,6 +126,16 @@ class StyleTokenLayer(torch.nn.Module):
             v = ops.gemm(tokens, m.linear_v.weight.detach(), m.linear_v.bias.detach())
             o = ops.gst_token_attention(q, k, v, m.h)
             return ops.gemm(o, m.linear_out.weight.detach(), m.linear_out.bias.detach())
+        if TRAINING_KERNELS and ref_embs.is_cuda:
+            from ... import autograd_fns as fns
+
+            m = self.mha
+            tokens = torch.tanh(self.gst_embs)
+            q = fns.linear(ref_embs, m.linear_q.weight, m.linear_q.bias, None, 1.0, None)
+            k = fns.linear(tokens, m.linear_k.weight, m.linear_k.bias, None, 1.0, None)
+            v = fns.linear(tokens, m.linear_v.weight, m.linear_v.bias, None, 1.0, None)
+            o = fns.gst_token_attention(q, k, v, m.h)
+            return fns.linear(o, m.linear_out.weight, m.linear_out.bias, None, 1.0, None)
         batch_size = ref_embs.size(0)
         gst_embs = torch.tanh(self.gst_embs).unsqueeze(0).expand(batch_size, -1, -1)
         return self.mha(ref_embs.unsqueeze(1), gst_embs, gst_embs, None).squeeze(1)

@@ -591,6 +591,70 @@ def conv2d_s2_bn_relu(x, w_packed, scale, shift, cw_layout: bool = False):
     return y
 
 
+def conv2d_s2_raw(x, w_packed):
+    """Pre-BatchNorm output of a ReferenceEncoder block (training path): [B,H,W,Ci] → [B,Ho,Wo,Co]."""
+    x = _f32(x, "x")
+    B, H, W, Ci = x.shape
+    Co = w_packed.shape[-1]
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Co), dtype=torch.float32, device=x.device)
+    check(lib().fs2k_conv2d_s2_bn_relu(_p(x), _p(_f32(w_packed, "w")), None, None, B, H, W, Ci, Co, 0, _p(y), _stream()),
+          "fs2k_conv2d_s2_bn_relu")
+    _count()
+    return y
+
+
+def conv2d_s2_dgrad(gz, w_packed, x_shape):
+    gz = _f32(gz, "gz")
+    B, H, W, Ci = x_shape
+    Co = w_packed.shape[-1]
+    dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gz.device)
+    check(lib().fs2k_conv2d_s2_dgrad(_p(gz), _p(_f32(w_packed, "w")), B, H, W, Ci, Co, _p(dx), _stream()), "fs2k_conv2d_s2_dgrad")
+    _count()
+    return dx
+
+
+def conv2d_s2_wgrad(x, gz):
+    """[3,3,Ci,Co] weight gradient of the stride-2 3×3 convolution."""
+    x, gz = _f32(x, "x"), _f32(gz, "gz")
+    B, H, W, Ci = x.shape
+    Co = gz.shape[-1]
+    dw = torch.empty((3, 3, Ci, Co), dtype=torch.float32, device=x.device)
+    check(lib().fs2k_conv2d_s2_wgrad(_p(x), _p(gz), B, H, W, Ci, Co, _p(dw), _stream()), "fs2k_conv2d_s2_wgrad")
+    _count()
+    return dw
+
+
+def gru_gate(xp, t: int, T: int, hp, h):
+    """One GRU cell update from xp [B·T, 3U] (step t of T) and hp = W_hh·h + b_hh."""
+    B, U = h.shape
+    h_new = torch.empty_like(h)
+    check(lib().fs2k_gru_gate(xp.data_ptr() + 4 * t * 3 * U, T * 3 * U, _p(hp), _p(h), B, U, _p(h_new), _stream()), "fs2k_gru_gate")
+    _count()
+    return h_new
+
+
+def gru_gate_bwd(xp, dxp, t: int, T: int, hp, h, dh):
+    """Cell backward of step t: fills dxp[:, t] and returns (d_hp [B,3U], dh·z [B,U])."""
+    B, U = h.shape
+    dhp = torch.empty_like(hp)
+    dh_prev = torch.empty_like(h)
+    off = 4 * t * 3 * U
+    check(lib().fs2k_gru_gate_bwd(xp.data_ptr() + off, T * 3 * U, _p(hp), _p(h), _p(_f32(dh, "dh")), B, U, dxp.data_ptr() + off,
+                                  T * 3 * U, _p(dhp), _p(dh_prev), _stream()), "fs2k_gru_gate_bwd")
+    _count()
+    return dhp, dh_prev
+
+
+def gst_token_attention_bwd(q, k, v, dout, heads: int):
+    q, k, v, dout = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(dout, "dout")
+    B, D = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    check(lib().fs2k_gst_token_attention_bwd(_p(q), _p(k), _p(v), _p(dout), B, k.shape[0], heads, D // heads, _p(dq), _p(dk), _p(dv),
+                                             _stream()), "fs2k_gst_token_attention_bwd")
+    _count()
+    return dq, dk, dv
+
+
 def gru_last_hidden(x, w_ih, w_hh, b_ih, b_hh):
     """Last hidden state [B,U] of a one-layer batch_first torch.nn.GRU over x [B,T,I], h0 = 0."""
     x = _f32(x, "x")

@@ -261,6 +261,17 @@ int fs2k_aligner_bwd(const float* g_soft, const float* g_logprob, const float* s
  * gst_token_attention: multi-head attention of one query per batch row over T <= 32 tokens (gst/attn.py:172-194). */
 int fs2k_conv2d_s2_bn_relu(const float* x, const float* w_khwcico, const float* scale, const float* shift, int B, int H,
                            int W, int Ci, int Co, int cw_layout, float* y, fs2k_stream_t stream);
+/* training through the reference encoder: scale == shift == NULL in conv2d_s2_bn_relu gives the raw (pre-BatchNorm) conv;
+ * its data / weight gradients (dw zeroed here, [3][3][Ci][Co]); GRU cell backward (d_xproj / d_hproj [B,3U], dh_prev = dh*z;
+ * the W_hh term is the caller's GEMM); token-attention backward (dk / dv zeroed here, summed over the batch). */
+int fs2k_conv2d_s2_dgrad(const float* gz, const float* w_khwcico, int B, int H, int W, int Ci, int Co, float* dx,
+                         fs2k_stream_t stream);
+int fs2k_conv2d_s2_wgrad(const float* x, const float* gz, int B, int H, int W, int Ci, int Co, float* dw_khwcico,
+                         fs2k_stream_t stream);
+int fs2k_gru_gate_bwd(const float* xproj, long xproj_row_stride, const float* hproj, const float* h, const float* dh, int B,
+                      int U, float* dxproj, long dxproj_row_stride, float* dhproj, float* dh_prev, fs2k_stream_t stream);
+int fs2k_gst_token_attention_bwd(const float* q, const float* k, const float* v, const float* dout, int B, int T, int heads,
+                                 int dk, float* dq, float* dk_out, float* dv_out, fs2k_stream_t stream);
 int fs2k_gru_gate(const float* xproj, long xproj_row_stride, const float* hproj, const float* h, int B, int U, float* h_out,
                   fs2k_stream_t stream);
 int fs2k_gst_token_attention(const float* q, const float* k, const float* v, int B, int T, int heads, int dk, float* out,

@@ -294,3 +294,37 @@ def test_ctc_forward_sum_kernel_matches_torch_ctc(B, F, T, case):
         assert float(ggpu[b, 0, :, int(key_lens[b]):].abs().max() if int(key_lens[b]) < T else 0.0) == 0.0
     if case == "impossible":
         assert float(ggpu[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,F", [(4, 130), (8, 500)])
+def test_gst_style_encoder_training_kernels_match_fp64_autograd(B, F):
+    """Training through the GST StyleEncoder on libfs2k kernels (raw conv + BatchNorm batch statistics + ReLU, GRU with
+    BPTT, token attention) against torch autograd over the same module in float64 on the CPU (the GPU library path runs
+    its convolutions in TF32 by default and is itself 1e-2 away): output, every parameter gradient, BatchNorm running
+    statistics."""
+    import copy
+
+    from fastspeech2_lightning_b200.fs2.gst import model as gst
+
+    torch.manual_seed(F)
+    ours = gst.StyleEncoder(idim=80).train()
+    ref = copy.deepcopy(ours).double()
+    ours = ours.to(DEV)
+    speech = torch.randn(B, F, 80)
+    go = torch.randn(B, 256)
+    y_ref = ref(speech.double())  # CPU tensors take the library path
+    y_ref.backward(go.double())
+    assert gst.TRAINING_KERNELS
+    y = ours(speech.to(DEV))
+    y.backward(go.to(DEV))
+    close(y.detach(), y_ref.detach(), 1e-4, "style embedding (training mode)")
+    for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        scale = float(q.grad.abs().max())
+        err = float((p.grad.cpu().double() - q.grad).abs().max())
+        assert err <= 1e-3 * max(scale, 1e-9) + 1e-7, (n, err, scale)
+    for (n, b1), (_, b2) in zip(ours.named_buffers(), ref.named_buffers()):
+        if b1.is_floating_point():
+            close(b1, b2, 1e-4, n)
+        else:
+            assert torch.equal(b1.cpu(), b2), n
