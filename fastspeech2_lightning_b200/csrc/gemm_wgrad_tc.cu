@@ -199,6 +199,13 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int N, i
 
 using namespace fs2k;
 
+// shared with gemm_wgrad_bf16.cu (declared in tc_common.cuh)
+int fs2k::wgrad_reduce_launch(const float* ws, int splits, int taps, int N, int K, int accumulate, float* out, cudaStream_t s) {
+    const long total4 = ((long)N * K * taps) >> 2;
+    fs2k_launch(wgrad_reduce_kernel, dim3((int)((total4 + 31) / 32)), dim3(256), 0, s, ws, splits, taps, N, K, accumulate, out);
+    return 0;
+}
+
 static void wgrad_tc_plan(int B, int L, int N, int K, int taps, int* tile_k, int* splits, int* chunks_per_split) {
     *tile_k = K >= 256 ? 256 : K;
     const int chunks_per_b = (L + WG_ROWS - 1) / WG_ROWS;

@@ -87,5 +87,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// out (parameter layout) (+)= Σ_split ws[split][tap][n][k] in a fixed order (gemm_wgrad_tc.cu); N·K must be a multiple of 4
+int wgrad_reduce_launch(const float* ws, int splits, int taps, int N, int K, int accumulate, float* out, cudaStream_t s);
 
 }  // namespace fs2k

@@ -443,6 +443,94 @@ def _gemm_f32(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act
     return c
 
 
+# ---------------------------------------------------------------------------------------------
+# bf16 arithmetic mode (gemm_bf16.cu / gemm_wgrad_bf16.cu)
+# ---------------------------------------------------------------------------------------------
+def cast_bf16(x, want_lo: bool = False):
+    """fp32 → (hi = bf16(x), lo = bf16(x − hi) or None)."""
+    x = _f32(x, "x")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_lo else None
+    check(lib().fs2k_cast_bf16(_p(x), x.numel(), _p(hi), _p(lo), _stream()), "fs2k_cast_bf16")
+    _count()
+    return hi, lo
+
+
+def gemm_bf16(a, w_hi, bias=None, *, w_lo=None, w_mn: bool = False, taps_pad: int = 0, scale=None, shift=None, act=None,
+              alpha: float = 1.0, residual=None, row_mask=None, want_c: bool = True, want_c16: bool = False,
+              want_pre: str | None = None, dropout_p: float = 0.0, seed: int = 0, block_n_hint: int = 0, out=None):
+    """a [B,L,K] / [M,K] (fp32, rounded in the kernel, or bf16) · bf16 weights, fp32 accumulate + fp32 epilogue.
+
+    w_mn=False: w_hi [taps,N,K] (or [N,K]).  w_mn=True: w_hi [taps,K,N] read MN-major, taps reversed (data gradient).
+    w_lo: bf16(W − w_hi) → hi·hi + hi·lo + lo·hi.  Returns (C fp32 | None, C16 bf16 | None, pre | None)."""
+    if not a.is_cuda:
+        raise ValueError("a must be a CUDA tensor (no CPU path)")
+    a_is_bf16 = a.dtype == torch.bfloat16
+    if not a_is_bf16:
+        a = _f32(a, "a")
+    elif not a.is_contiguous():
+        a = a.contiguous()
+    if a.dim() == 2:
+        B, L, K = 1, a.shape[0], a.shape[1]
+        out_shape = (L,)
+    else:
+        B, L, K = a.shape
+        out_shape = (B, L)
+    assert w_hi.dtype == torch.bfloat16 and w_hi.is_contiguous()
+    if w_hi.dim() == 2:
+        w_hi = w_hi.reshape(1, *w_hi.shape)
+        if w_lo is not None:
+            w_lo = w_lo.reshape(1, *w_lo.shape)
+    taps = w_hi.shape[0]
+    if w_mn:
+        assert w_hi.shape[1] == K, (w_hi.shape, K)
+        N = w_hi.shape[2]
+    else:
+        assert w_hi.shape[2] == K, (w_hi.shape, K)
+        N = w_hi.shape[1]
+    if not lib().fs2k_gemm_bf16_supported(K, N, K, taps, int(a_is_bf16), int(w_mn)):
+        raise ValueError(f"fs2k_gemm_bf16 does not take K={K} N={N} taps={taps} bf16_a={a_is_bf16} w_mn={w_mn}")
+    dev = a.device
+    c = out if out is not None else (torch.empty((*out_shape, N), dtype=torch.float32, device=dev) if want_c else None)
+    c16 = torch.empty((*out_shape, N), dtype=torch.bfloat16, device=dev) if want_c16 else None
+    pre = None
+    if want_pre is not None:
+        pre = torch.empty((*out_shape, N), dtype=torch.float32 if want_pre == "fp32" else torch.bfloat16, device=dev)
+    if residual is not None:
+        residual = _f32(residual, "residual")
+    if row_mask is not None:
+        row_mask = row_mask.contiguous()
+    check(lib().fs2k_gemm_bf16(_p(a), int(a_is_bf16), K, B, L, K, _p(w_hi), _p(w_lo), int(w_mn), N, taps, taps_pad, _p(bias),
+                               _p(scale), _p(shift), _ACTS[act], float(alpha), _p(residual), N, _p(row_mask), _p(c), N, _p(c16), N,
+                               _p(pre) if want_pre == "fp32" else None, _p(pre) if want_pre == "bf16" else None, N,
+                               float(dropout_p), int(seed), int(block_n_hint), _stream()), "fs2k_gemm_bf16")
+    _count()
+    return c, c16, pre
+
+
+def gemm_wgrad_bf16(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=None):
+    """bf16-mode weight gradient: g [B,L,N], x [B,L,K] fp32 → [N,K,taps] (conv_layout) or [N,K]; None when unsupported."""
+    g, x = _f32(g, "g"), _f32(x, "x")
+    if g.dim() == 2:
+        B, L = 1, g.shape[0]
+    else:
+        B, L = g.shape[0], g.shape[1]
+    N, K = g.shape[-1], x.shape[-1]
+    if B * L == 0 or not lib().fs2k_gemm_wgrad_bf16_supported(N, K, N, K):
+        return None
+    ws_bytes = lib().fs2k_gemm_wgrad_bf16_workspace_bytes(B, L, N, K, taps)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+    acc = accumulate_into is not None and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
+    out = accumulate_into if acc else torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
+    assert out.numel() == N * K * taps
+    check(lib().fs2k_gemm_wgrad_bf16(_p(g), N, _p(x), K, B, L, N, K, taps, pad, _p(ws), ws_bytes, _p(out), int(acc), _stream()),
+          "fs2k_gemm_wgrad_bf16")
+    _count(2)
+    if accumulate_into is not None and not acc:
+        accumulate_into.add_(out)
+    return out
+
+
 def rowdot(x, w, b=None, mask=None):
     x = _f32(x, "x")
     D = x.shape[-1]

@@ -142,6 +142,34 @@ int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, i
                  const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, const float* ln_gamma,
                  const float* ln_beta, float ln_eps, float* ln_out, const float* ln2_gamma, const float* ln2_beta,
                  float* ln2_out, float dropout_p, long seed, int passes, const float* W_small, fs2k_stream_t stream);
+/* bf16 arithmetic mode (BASELINE configs[2]; gemm_bf16.cu): tcgen05.mma kind::f16 — operands rounded to bf16,
+ * fp32 accumulation in TMEM, fp32 epilogue.  Same contraction contract as fs2k_gemm_f32 with
+ *   A: fp32 (a_is_bf16 = 0; rounded in the kernel, no cast pass) or bf16 (a_is_bf16 = 1; TMA), row stride lda elements
+ *   W_hi: bf16 weights; W_lo (optional, fp32 A only): bf16(W - W_hi) — the kernel then also splits A and accumulates
+ *         hi*hi + hi*lo + lo*hi (fp32-level accuracy)
+ *   w_mn = 0: W is [taps][N][K];  w_mn = 1: W is [taps][K][N] read MN-major with the taps visited in reverse — the
+ *         data-gradient GEMM dX = G * W of a layer whose forward weights are that same array (no transposed copy)
+ *   outputs (each optional, at least one): C fp32 / C16 bf16 = the final value; P32 / P16 (stride ldp) = acc + bias,
+ *         the pre-activation saved for the backward.
+ * block_n_hint: 0 = automatic column tile; 256 = wide tile for compute-bound shapes.
+ * fs2k_gemm_bf16_supported: K % 8 == 0 (w_mn = 0) / N % 8 == 0 (w_mn = 1), lda % 4 == 0 (fp32 A) or % 8 (bf16 A),
+ * N % 16 == 0 (N <= 256) or N % 128 == 0. */
+int fs2k_gemm_bf16_supported(int K, int N, int lda, int taps, int a_is_bf16, int w_mn);
+int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int L, int K, const void* W_hi, const void* W_lo,
+                   int w_mn, int N, int taps, int pad, const float* bias, const float* scale, const float* shift,
+                   int act, float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
+                   void* C16, int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, int block_n_hint,
+                   fs2k_stream_t stream);
+/* hi[i] = bf16(x[i]); lo[i] = bf16(x[i] - hi[i]) when lo != NULL */
+int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream);
+/* Weight gradient in the bf16 mode (gemm_wgrad_bf16.cu): G, X fp32 in HBM, rounded to bf16 in the kernel, both read as
+ * MN-major tcgen05 operands, fp32 accumulation; same outputs as fs2k_gemm_wgrad_tc.  N % 4 == 0, K % 16 == 0,
+ * K <= 256 or K % 256 == 0. */
+int fs2k_gemm_wgrad_bf16_supported(int N, int K, int ldg, int ldx);
+size_t fs2k_gemm_wgrad_bf16_workspace_bytes(int B, int L, int N, int K, int taps);
+int fs2k_gemm_wgrad_bf16(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps,
+                         int pad, void* workspace, size_t workspace_bytes, float* dW_param_layout, int accumulate,
+                         fs2k_stream_t stream);
 /* out[i] = x[i] - tf32_truncate(x[i]): the "small" operand of the 3xTF32 scheme */
 int fs2k_split_small(const float* x, long n, float* out, fs2k_stream_t stream);
 int fs2k_rowdot(const float* x, const float* w, const float* b, const uint8_t* mask, long M, int D, float* y,

@@ -1,0 +1,137 @@
+"""bf16 arithmetic mode: op-level checks of the tcgen05 kind::f16 kernels (through the C ABI).
+
+Reference = a plain PyTorch fp32 contraction of the SAME bf16-rounded operands (so only the fp32 accumulation order
+differs: tolerance 2e-5 of max|ref|), plus the stated bf16 bar against the un-rounded fp32 contraction."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ACC_TOL = 2e-5     # fp32 accumulation-order noise, relative to max|ref|
+BF16_TOL = 1e-2    # bf16-rounded operands vs the fp32 contraction (north_star: bf16 mel L1 <= 1e-2)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def ops():
+    from fastspeech2_lightning_b200 import ops as o
+
+    return o
+
+
+def r16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def rel(got, want):
+    return float((got.double() - want.double()).abs().max() / want.double().abs().max().clamp_min(1e-6))
+
+
+def conv_ref(a, w_taps, pad):
+    """a [B,L,K], w_taps [taps,N,K] → [B,L,N] (fp64 on the GPU: exact reference of the given operands)."""
+    w = w_taps.permute(1, 2, 0).double()  # [N,K,taps]
+    return F.conv1d(a.double().transpose(1, 2), w, None, padding=pad).transpose(1, 2)
+
+
+def rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev())
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 256, 256), (1000, 256, 1024), (777, 1024, 256), (513, 256, 768), (200, 80, 512), (260, 512, 80), (96, 256, 32)])
+def test_gemm_bf16_linear(M, K, N):
+    a, w = rand(M, K, seed=1), rand(N, K, seed=2, scale=K ** -0.5)
+    bias = rand(N, seed=3, scale=0.1)
+    w16, _ = ops().cast_bf16(w)
+    c, _, _ = ops().gemm_bf16(a, w16, bias)
+    want = (r16(a).double() @ r16(w).double().T + bias.double()).float()
+    assert rel(c, want) <= ACC_TOL, rel(c, want)
+    assert rel(c, (a.double() @ w.double().T + bias.double()).float()) <= BF16_TOL
+
+
+def test_gemm_bf16_epilogue_outputs():
+    M, K, N = 500, 256, 1024
+    a, w, bias, res = rand(M, K, seed=1), rand(N, K, seed=2, scale=K ** -0.5), rand(N, seed=3, scale=0.1), rand(M, N, seed=4)
+    mask = (torch.arange(M, device=dev()) % 7 != 0)
+    w16, _ = ops().cast_bf16(w)
+    c, c16, pre = ops().gemm_bf16(a, w16, bias, act="silu", alpha=0.5, residual=res, row_mask=mask, want_c16=True, want_pre="fp32")
+    z = (r16(a).double() @ r16(w).double().T + bias.double())
+    want = ((F.silu(z) * 0.5 + res.double()) * mask[:, None]).float()
+    assert rel(pre, z.float()) <= ACC_TOL
+    assert rel(c, want) <= ACC_TOL
+    assert torch.equal(c16, c.to(torch.bfloat16))
+    _, _, pre16 = ops().gemm_bf16(a, w16, bias, act="relu", want_c=False, want_c16=True, want_pre="bf16")
+    assert torch.equal(pre16, pre.to(torch.bfloat16))
+
+
+def test_gemm_bf16_a_in_bf16_by_tma():
+    M, K, N = 700, 1024, 256
+    a, w = rand(M, K, seed=5), rand(N, K, seed=6, scale=K ** -0.5)
+    w16, _ = ops().cast_bf16(w)
+    a16, _ = ops().cast_bf16(a)
+    c, _, _ = ops().gemm_bf16(a16, w16, None)
+    want = (r16(a).double() @ r16(w).double().T).float()
+    assert rel(c, want) <= ACC_TOL, rel(c, want)
+
+
+@pytest.mark.parametrize("B,L,K,N,taps", [(3, 200, 512, 512, 5), (2, 333, 80, 512, 5), (4, 150, 512, 80, 5), (2, 90, 256, 256, 3)])
+@pytest.mark.parametrize("a_bf16", [False, True])
+def test_gemm_bf16_conv_taps(B, L, K, N, taps, a_bf16):
+    a, w = rand(B, L, K, seed=7), rand(taps, N, K, seed=8, scale=(K * taps) ** -0.5)
+    w16, _ = ops().cast_bf16(w)
+    pad = (taps - 1) // 2
+    src = ops().cast_bf16(a)[0] if a_bf16 else a
+    c, _, _ = ops().gemm_bf16(src, w16, None, taps_pad=pad, block_n_hint=256 if N % 256 == 0 else 0)
+    want = conv_ref(r16(a), r16(w), pad).float()
+    assert rel(c, want) <= ACC_TOL, rel(c, want)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 256, 256), (640, 256, 1024), (200, 1024, 256)])
+def test_gemm_bf16_split3_is_fp32_accurate(M, K, N):
+    a, w = rand(M, K, seed=9), rand(N, K, seed=10, scale=K ** -0.5)
+    hi, lo = ops().cast_bf16(w, want_lo=True)
+    c, _, _ = ops().gemm_bf16(a, hi, None, w_lo=lo)
+    want = (a.double() @ w.double().T).float()
+    assert rel(c, want) <= 5e-5, rel(c, want)   # hi·hi + hi·lo + lo·hi: the dropped lo·lo term is 2^-16 relative per product
+
+
+@pytest.mark.parametrize("M,Nf,Kf", [(300, 256, 256), (500, 1024, 256), (400, 256, 1024), (260, 80, 512), (200, 512, 80)])
+def test_gemm_bf16_dgrad_reads_weights_mn_major(M, Nf, Kf):
+    """dX[m,k] = Σ_n G[m,n]·W[n,k] with the forward weight array W [Nf,Kf] itself as the (MN-major) operand."""
+    g, w = rand(M, Nf, seed=11), rand(Nf, Kf, seed=12, scale=Nf ** -0.5)
+    w16, _ = ops().cast_bf16(w)
+    dx, _, _ = ops().gemm_bf16(g, w16.reshape(1, Nf, Kf), None, w_mn=True)
+    want = (r16(g).double() @ r16(w).double()).float()
+    assert rel(dx, want) <= ACC_TOL, rel(dx, want)
+
+
+@pytest.mark.parametrize("B,L,Nf,Kf,taps", [(3, 200, 512, 512, 5), (2, 170, 512, 80, 5), (2, 130, 80, 512, 5)])
+def test_gemm_bf16_conv_dgrad(B, L, Nf, Kf, taps):
+    g, w = rand(B, L, Nf, seed=13), rand(taps, Nf, Kf, seed=14, scale=(Nf * taps) ** -0.5)
+    pad = (taps - 1) // 2
+    w16, _ = ops().cast_bf16(w)
+    dx, _, _ = ops().gemm_bf16(g, w16, None, w_mn=True, taps_pad=taps - 1 - pad)
+    # transposed convolution = autograd of the forward convolution
+    x = torch.zeros(B, L, Kf, device=dev(), dtype=torch.float64, requires_grad=True)
+    y = conv_ref(x, r16(w), pad)
+    (want,) = torch.autograd.grad(y, x, r16(g).double())
+    assert rel(dx, want.float()) <= ACC_TOL, rel(dx, want.float())
+
+
+@pytest.mark.parametrize("B,L,N,K,taps", [(4, 300, 256, 256, 1), (3, 500, 1024, 256, 1), (3, 500, 256, 1024, 1), (2, 257, 512, 512, 5),
+                                           (2, 200, 512, 80, 5), (2, 200, 80, 512, 5), (1, 70, 768, 256, 1)])
+def test_gemm_wgrad_bf16(B, L, N, K, taps):
+    g, x = rand(B, L, N, seed=15), rand(B, L, K, seed=16)
+    pad = (taps - 1) // 2
+    dw = ops().gemm_wgrad_bf16(g, x, taps, pad, conv_layout=taps > 1)
+    assert dw is not None
+    w = torch.zeros(N, K, taps, device=dev(), dtype=torch.float64, requires_grad=True)
+    y = F.conv1d(r16(x).double().transpose(1, 2), w, None, padding=pad).transpose(1, 2)
+    (want,) = torch.autograd.grad(y, w, r16(g).double())
+    want = want.float() if taps > 1 else want[:, :, 0].float()
+    assert rel(dw, want) <= ACC_TOL, rel(dw, want)
+    acc = torch.ones_like(dw)
+    ops().gemm_wgrad_bf16(g, x, taps, pad, conv_layout=taps > 1, accumulate_into=acc)
+    assert rel(acc - 1.0, want) <= 1e-4
