@@ -121,8 +121,24 @@ def _direct_grads(*params):
     return [p.grad for p in params]
 
 
-def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight=None, bias=None, wt=None):
-    """Shared by every contraction: g = gradient w.r.t. the pre-activation conv output."""
+def _prefetch_wt(w_taps, needs_dx):
+    """Transposed weights for the data-gradient GEMM, re-packed on the side stream during the forward — not needed in
+    the bf16 mode, whose dgrad reads the forward weights as an MN-major operand."""
+    if _SINK is None or not needs_dx:
+        return None
+    if ops.PRECISION == "bf16" and ops.bf16_dgrad_ok(w_taps):
+        return None
+    return _SINK.prefetch_transposed(w_taps)
+
+
+def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight=None, bias=None, wt=None, precision=None):
+    """Shared by every contraction: g = gradient w.r.t. the pre-activation conv output.  `precision` = the arithmetic
+    mode the forward ran in (the backward of a full-precision region stays full precision in the bf16 mode)."""
+    with ops.precision_scope(precision):
+        return _gemm_backward_impl(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight, bias, wt)
+
+
+def _gemm_backward_impl(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, weight, bias, wt):
     taps, N, K = w_taps.shape
     dx = dw = db = None
     sink = _SINK
@@ -140,7 +156,7 @@ def _gemm_backward(g, x, w_taps, pad, conv_layout, needs_x, needs_w, needs_b, we
         db = ops.colsum(g)
     with ops.backward_precision():
         if needs_x:
-            dx = ops.gemm(g, wt if wt is not None else ops.weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
+            dx = ops.gemm_dgrad(g, w_taps, pad, wt)
         if needs_w:
             dw = ops.gemm_wgrad(g, x, taps, pad, conv_layout)
     return dx, dw, db
@@ -157,9 +173,8 @@ class _Gemm(torch.autograd.Function):
         aux = None
         seed = _seed(p)
         ctx.drop = (p, seed)
-        if act == "silu":  # keep the pre-activation for silu'; SiLU (+ Dropout) in one elementwise launch
-            aux = ops.gemm(x, w_taps, bias, taps_pad=pad)
-            y = ops.affine_act(aux, None, None, "silu", residual, dropout_p=p, seed=seed)
+        if act == "silu":  # keep the pre-activation for silu'; SiLU (+ Dropout) fused (bf16 mode: into the GEMM epilogue)
+            aux, y = ops.gemm_silu_pair(x, w_taps, bias, pad, residual, p, seed)
             if alpha != 1.0:
                 raise NotImplementedError("alpha with silu")
         elif p:
@@ -176,7 +191,8 @@ class _Gemm(torch.autograd.Function):
         ctx.save_for_backward(x, w_taps, aux)
         ctx.meta = (act, alpha, pad, conv_layout, bias is not None, residual is not None)
         ctx.params = (weight, bias)
-        ctx.wt = _SINK.prefetch_transposed(w_taps) if (_SINK is not None and ctx.needs_input_grad[0]) else None
+        ctx.precision = ops.PRECISION
+        ctx.wt = _prefetch_wt(w_taps, ctx.needs_input_grad[0])
         return y
 
     @staticmethod
@@ -187,7 +203,7 @@ class _Gemm(torch.autograd.Function):
         g = g.contiguous()
         gz = g if (act is None and alpha == 1.0 and not ctx.drop[0]) else ops.act_bwd(g, aux, act, alpha, None, *ctx.drop)
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, conv_layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt)
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt, precision=ctx.precision)
         return dx, dw, db, (g if has_res and ctx.needs_input_grad[3] else None), None, None, None
 
 
@@ -223,7 +239,8 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.meta = (act, training, pad, bias is not None, p, seed)
         ctx.params = (weight, bias)
         ctx.bn_params = (bn_w, bn_b)
-        ctx.wt = _SINK.prefetch_transposed(w_taps) if (_SINK is not None and ctx.needs_input_grad[0]) else None
+        ctx.precision = ops.PRECISION
+        ctx.wt = _prefetch_wt(w_taps, ctx.needs_input_grad[0])
         return y
 
     @staticmethod
@@ -236,7 +253,7 @@ class _ConvBnAct(torch.autograd.Function):
         if direct is not None:
             dgamma = dbeta = None
         dx, dw, db = _gemm_backward(gz, x, w_taps, pad, True, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt)
+                                    has_bias and ctx.needs_input_grad[2], *ctx.params, wt=ctx.wt, precision=ctx.precision)
         return dx, dw, db, dgamma, dbeta, None, None, None, None
 
 
@@ -679,11 +696,17 @@ class _GruLastHidden(torch.autograd.Function):
             h = ops.gru_gate(xp, t, T, hp, h)
         ctx.save_for_backward(x2, w_ih, w_hh, xp, torch.stack(hs), torch.stack(hps))
         ctx.shape = (B, T, I, U)
+        ctx.precision = ops.PRECISION
         return h
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dh):
+        with ops.precision_scope(ctx.precision):
+            return _GruLastHidden._backward(ctx, dh)
+
+    @staticmethod
+    def _backward(ctx, dh):
         x2, w_ih, w_hh, xp, hs, hps = ctx.saved_tensors
         B, T, I, U = ctx.shape
         dxp = torch.empty_like(xp)

@@ -1,6 +1,8 @@
 // Training-step tail over one flat parameter buffer: global gradient norm, norm clipping and AdamW in two
 // launches (reference: torch.optim.AdamW at fs2/model.py:530-537, gradient_clip_val = 1.0 at fs2/cli/train.py:38,
 // which Lightning applies as clip_grad_norm_).  The clip coefficient stays on the device — no host sync.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fs2k {
@@ -31,7 +33,8 @@ sumsq_kernel(const float* __restrict__ g, long N, double* __restrict__ out) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long N,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
-             float grad_scale, const double* __restrict__ sumsq, const float* __restrict__ step_state) {
+             float grad_scale, const double* __restrict__ sumsq, const float* __restrict__ step_state,
+             __nv_bfloat16* __restrict__ p16) {
     pdl_prologue();
     if (step_state) {  // graph replay: the step's scalars come from device memory
         lr = step_state[0];
@@ -52,7 +55,9 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] * (1.f - lr * wd) - step_size * (mi / denom);
+        const float pi = p[i] * (1.f - lr * wd) - step_size * (mi / denom);
+        p[i] = pi;
+        if (p16) p16[i] = __float2bfloat16_rn(pi);  // bf16 shadow of the weights: the bf16-mode GEMM operands, no cast pass
     }
 }
 
@@ -77,7 +82,7 @@ extern "C" int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t str
 
 extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float lr, float beta1, float beta2,
                                float eps, float weight_decay, long step, float max_norm, float grad_scale,
-                               const double* sumsq, fs2k_stream_t stream) {
+                               const double* sumsq, void* p_bf16, fs2k_stream_t stream) {
     FS2K_REQUIRE(N >= 0 && step >= 1, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(p && g && m && v, FS2K_ERR_NULL);
@@ -86,21 +91,21 @@ extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, lon
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     fs2k_launch(adamw_kernel, dim3((int)grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                             bc2_sqrt, max_norm, grad_scale, sumsq, nullptr);
+                                                             bc2_sqrt, max_norm, grad_scale, sumsq, nullptr, (__nv_bfloat16*)p_bf16);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }
 
 extern "C" int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v, long N, const float* step_state,
                                    float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                                   float grad_scale, const double* sumsq, fs2k_stream_t stream) {
+                                   float grad_scale, const double* sumsq, void* p_bf16, fs2k_stream_t stream) {
     FS2K_REQUIRE(N >= 0, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(p && g && m && v && step_state, FS2K_ERR_NULL);
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     fs2k_launch(adamw_kernel, dim3((int)grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, N, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
-                                                             max_norm, grad_scale, sumsq, step_state);
+                                                             max_norm, grad_scale, sumsq, step_state, (__nv_bfloat16*)p_bf16);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -169,18 +169,21 @@ class FastSpeech2(_Base):
             text_inputs = batch["text"]
             inputs, x = fns.embed_posenc(text_inputs[:, :max_src_len], self.text_input_layer.weight, inv_freq, src_lens,
                                          self.text_input_layer.padding_idx)
+        if ops.PRECISION == "bf16":
+            ops.refresh_bf16_shadows(self.parameters())  # bf16 weight operands current (one check per forward)
         # encoder (:193)
         x, _ = self.encoder(x, src_lens)
 
         # style / speaker / language rows, broadcast over T (:196-213)
         rows = []
         if m.use_global_style_token_module:
-            if inference and torch.is_tensor(batch["mel_style_reference"]):
-                rows.append((self.gst(batch["mel_style_reference"]), None))
-            elif inference and not teacher_forcing:
-                rows.append((self.gst.condition_on_gst_tokens(batch["text"].size(0)), None))
-            else:
-                rows.append((self.gst(batch["mel"]), None))
+            with ops.full_precision():
+                if inference and torch.is_tensor(batch["mel_style_reference"]):
+                    rows.append((self.gst(batch["mel_style_reference"]), None))
+                elif inference and not teacher_forcing:
+                    rows.append((self.gst.condition_on_gst_tokens(batch["text"].size(0)), None))
+                else:
+                    rows.append((self.gst(batch["mel"]), None))
         if m.multispeaker and self.speaker_embedding is not None:
             rows.append((self.speaker_embedding.weight, batch["speaker_id"]))
         if m.multilingual and self.language_embedding is not None:
@@ -188,8 +191,10 @@ class FastSpeech2(_Base):
         if rows:
             x = fns.add_rows(x, rows)
 
-        va = self.variance_adaptor(inputs, x, batch, src_mask, control, inference=inference,
-                                   teacher_forcing=teacher_forcing, inv_freq=inv_freq)
+        # aligner → MAS, predictors → bucketize / durations: discrete decisions, fp32-level arithmetic in every mode
+        with ops.full_precision():
+            va = self.variance_adaptor(inputs, x, batch, src_mask, control, inference=inference,
+                                       teacher_forcing=teacher_forcing, inv_freq=inv_freq)
         tgt_mask = va["target_mask"]
         if inference and not teacher_forcing:  # :226-230
             mel_lens = ops.mask_lens(tgt_mask)
@@ -283,6 +288,7 @@ class FastSpeech2(_Base):
         if use_cuda_graph:
             return runner(batch)
         dev = self.optimizer.flat_p.device
+        runner._arm_seed_base()
         losses = runner._step_body({k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()})
         self.scheduler.step()
         return losses

@@ -8,14 +8,36 @@ i.e. given durations (teacher-forced synthesis) with `validate_durations = False
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
-from ._lib import lib
+from ._lib import check, lib
+
+_ARMED_SEED_BASE = 0  # device address the library's dropout seed-base pointer currently holds (0 = none)
+
+
+def _clear_seed_base(ptr: int) -> None:
+    """The counter's owner is gone: a dangling pointer would make every later dropout kernel read freed memory."""
+    global _ARMED_SEED_BASE
+    if _ARMED_SEED_BASE == ptr:
+        try:
+            lib().fs2k_set_dropout_seed_base(None)
+        except Exception:
+            pass
+        _ARMED_SEED_BASE = 0
 
 
 def _signature(batch) -> tuple:
-    sig = []
+    """Shape signature of the model's input keys.  Private keys (`_staging`, the packed host blob collate_to_device adds,
+    whose size depends on the valid lengths) are not inputs of the model and stay out of the key — and out of the
+    captured input buffers."""
+    from . import ops
+
+    sig = [("precision", ops.PRECISION, ops.BACKWARD_PRECISION, ops.DECODER_PRECISION)]
     for k in sorted(batch):
+        if k.startswith("_"):
+            continue
         v = batch[k]
         if torch.is_tensor(v) and v.dim() > 0:
             sig.append((k, tuple(v.shape), str(v.dtype)))
@@ -32,7 +54,8 @@ class GraphedSynthesis:
 
     def _capture(self, batch):
         model = self.model
-        static_in = {k: (v.clone() if torch.is_tensor(v) and v.dim() > 0 and v.is_cuda else v) for k, v in batch.items()}
+        static_in = {k: (v.clone() if torch.is_tensor(v) and v.dim() > 0 and v.is_cuda else v) for k, v in batch.items()
+                     if not k.startswith("_")}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -54,12 +77,12 @@ class GraphedSynthesis:
             if len(self._cache) >= self.max_graphs:
                 self._cache.pop(next(iter(self._cache)))
             dev = next(self.model.parameters()).device
-            dev_batch = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+            dev_batch = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items() if not k.startswith("_")}
             entry = self._capture(dev_batch)
             self._cache[key] = entry
         graph, static_in, static_out = entry
         for k, v in batch.items():
-            if torch.is_tensor(v) and v.dim() > 0:
+            if torch.is_tensor(v) and v.dim() > 0 and k in static_in:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         graph.replay()
         return static_out
@@ -89,7 +112,20 @@ class GraphedTrainStep:
         self._pool = None
         self.overlap_wgrad = overlap_wgrad
         self._sink = None
-        lib().fs2k_set_dropout_seed_base(optimizer.seed_base.data_ptr())
+        # every dropout kernel adds *seed_base to its by-value seed (fresh masks on graph replays).  The pointer is
+        # process-wide inside the library: it is re-armed before every step of THIS runner (another runner may have
+        # pointed it at its own counter) and cleared when the optimizer — the owner of the counter — goes away.
+        self._arm_seed_base()
+        weakref.finalize(optimizer, _clear_seed_base, optimizer.seed_base.data_ptr())
+
+    def _arm_seed_base(self) -> None:
+        global _ARMED_SEED_BASE
+        ptr = self.opt.seed_base.data_ptr()
+        if _ARMED_SEED_BASE != ptr:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the dropout seed base must be armed before the capture starts")
+            check(lib().fs2k_set_dropout_seed_base(ptr), "fs2k_set_dropout_seed_base")
+            _ARMED_SEED_BASE = ptr
 
     def _step_body(self, batch, update: bool = True):
         from . import autograd_fns as fns
@@ -128,13 +164,15 @@ class GraphedTrainStep:
         """batch: collated dict (CUDA or pinned-host tensors).  Returns the dict of loss tensors (device scalars;
         static buffers of the graph — read or copy them before the next call)."""
         model, opt = self.model, self.opt
+        self._arm_seed_base()
         key = self._key(batch)
         entry = self._cache.get(key)
         dev = opt.flat_p.device
         if entry is None and (key not in self._seen or key in self._eager_only):
             # first sight of this shape: plain eager step (validates the data, warms every lazy init)
             self._seen.add(key)
-            dev_batch = {k: (v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+            dev_batch = {k: (v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()
+                         if not k.startswith("_")}
             losses = self._step_body(dev_batch)
             if self.sched is not None:
                 self.sched.step()
@@ -142,7 +180,8 @@ class GraphedTrainStep:
         if entry is None:
             if len(self._cache) >= self.max_graphs:
                 self._cache.pop(next(iter(self._cache)))
-            static_in = {k: (v.to(dev).clone() if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+            static_in = {k: (v.to(dev).clone() if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()
+                         if not k.startswith("_")}
             va = model.variance_adaptor
             prev_validate, va.validate_durations = va.validate_durations, False  # the eager first sight validated
             opt.device_state = True
@@ -175,7 +214,7 @@ class GraphedTrainStep:
             self._cache[key] = entry
         graph, static_in, static_losses, graph2 = entry
         for k, v in batch.items():
-            if torch.is_tensor(v) and v.dim() > 0:
+            if torch.is_tensor(v) and v.dim() > 0 and k in static_in:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         opt.begin_graph_step()
         graph.replay()

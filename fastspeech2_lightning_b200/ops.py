@@ -285,6 +285,10 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
 #   "fp32"   exact FFMA kernel (gemm_simt.cu)
 #   "tf32x3" tcgen05 tensor cores, 3×TF32 split accumulation — fp32-level accuracy (default)
 #   "tf32"   tcgen05 tensor cores, single TF32 pass
+#   "bf16"   tcgen05 kind::f16: operands rounded to bf16, fp32 accumulation / epilogue / residual stream / norms /
+#            softmax / master weights (BASELINE configs[2]).  Applies to the Conformer stacks, mel_linear and PostNet;
+#            what feeds a discrete decision (aligner → MAS, variance predictors → bucketize / durations) runs under
+#            `full_precision()` and stays 3×TF32, so alignments, durations and teacher-forced bucket ids do not move.
 PRECISION = "tf32x3"
 
 
@@ -302,7 +306,7 @@ DECODER_PRECISION = None
 def set_precision(mode: str, backward: str | None = None, decoder: str | None = None) -> None:
     global PRECISION, BACKWARD_PRECISION, DECODER_PRECISION
     for m in (mode, backward, decoder):
-        if m not in (None, "fp32", "tf32", "tf32x3"):
+        if m not in (None, "fp32", "tf32", "tf32x3", "bf16"):
             raise ValueError(m)
     PRECISION = mode
     BACKWARD_PRECISION = backward
@@ -321,6 +325,34 @@ class decoder_precision:
     def __exit__(self, *a):
         global PRECISION
         PRECISION = self.prev
+
+
+class precision_scope:
+    """Run the enclosed contractions in `mode` (the autograd Functions re-enter their forward's mode in backward)."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        global PRECISION
+        self.prev = PRECISION
+        if self.mode is not None:
+            PRECISION = self.mode
+
+    def __exit__(self, *a):
+        global PRECISION
+        PRECISION = self.prev
+
+
+class full_precision(precision_scope):
+    """fp32-level arithmetic for whatever feeds a discrete decision: "bf16" is lifted to 3×TF32, other modes stay."""
+
+    def __init__(self):
+        super().__init__(None)
+
+    def __enter__(self):
+        self.mode = "tf32x3" if PRECISION == "bf16" else None
+        super().__enter__()
 
 
 class backward_precision:
@@ -345,6 +377,10 @@ def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None
     ln = (gamma, beta, eps): also return LayerNorm(result) — fused into the tensor-core epilogue when one
     tile spans the row, otherwise a separate fs2k_layernorm_fwd launch; ln2 = (gamma, beta) chains a second
     LayerNorm on the first one's output.  Returns C, or (C, ln_out[, ln2_out]) when ln is given."""
+    if PRECISION == "bf16" and ln is None:
+        r = _gemm_bf16_auto(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, dropout_p, seed)
+        if r is not None:
+            return r
     if ln is not None or PRECISION != "fp32":
         r = _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, ln, ln2, want_c, dropout_p, seed, w_small)
         if r is not None:
@@ -361,6 +397,55 @@ def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None
     if ln2 is None:
         return c, y
     return c, y, layernorm(y, ln2[0], ln2[1], ln[2])
+
+
+def _bf16_shape_ok(a, w, w_mn: bool) -> bool:
+    K = a.shape[-1]
+    taps = 1 if w.dim() == 2 else w.shape[0]
+    N = w.shape[-1] if w_mn else w.shape[-2]
+    return bool(lib().fs2k_gemm_bf16_supported(K, N, K, taps, int(a.dtype == torch.bfloat16), int(w_mn))) and not (a.data_ptr() & 15)
+
+
+def bf16_dgrad_ok(w_taps) -> bool:
+    """Can the bf16-mode data-gradient GEMM read these forward weights [taps,N,K] as its MN-major operand?"""
+    taps, N, K = w_taps.shape
+    return bool(lib().fs2k_gemm_bf16_supported(N, K, N, taps, 0, 1))
+
+
+def _gemm_bf16_auto(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, dropout_p, seed):
+    """The bf16-mode path of gemm(): fp32 weights `w` → their bf16 shadow / cached cast; None when the shape is not taken."""
+    if not _bf16_shape_ok(a, w, False):
+        return None
+    w16, _ = bf16_weight(w)
+    K = a.shape[-1]
+    taps = 1 if w.dim() == 2 else w.shape[0]
+    hint = 256 if taps * K >= 1024 and w16.shape[-2] % 256 == 0 else 0  # compute-bound shapes (PostNet): wide tiles
+    c, _, _ = gemm_bf16(a, w16, bias, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha, residual=residual,
+                        row_mask=row_mask, dropout_p=dropout_p, seed=seed, block_n_hint=hint, out=out)
+    return c
+
+
+def gemm_dgrad(g, w_taps, pad: int, wt=None):
+    """dX of y = conv(x, W): g [B,L,N] · W [taps,N,K] → [B,L,K].  bf16 mode: the forward weights themselves are the
+    (MN-major) operand; otherwise `wt` / a transposed re-pack feeds the forward kernel."""
+    taps = w_taps.shape[0]
+    if PRECISION == "bf16" and bf16_dgrad_ok(w_taps) and not (g.data_ptr() & 15):
+        w16, _ = bf16_weight(w_taps)
+        hint = 256 if taps * w_taps.shape[1] >= 1024 and w_taps.shape[2] % 256 == 0 else 0
+        return gemm_bf16(g, w16, None, w_mn=True, taps_pad=taps - 1 - pad, block_n_hint=hint)[0]
+    return gemm(g, wt if wt is not None else weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
+
+
+def gemm_silu_pair(a, w, bias, taps_pad: int = 0, residual=None, dropout_p: float = 0.0, seed: int = 0):
+    """(pre, y): pre = conv(a, W) + b, y = dropout(silu(pre)) + residual — one launch in the bf16 mode (the epilogue
+    writes both), else the GEMM followed by the fused SiLU + dropout elementwise kernel."""
+    if PRECISION == "bf16" and _bf16_shape_ok(a, w, False):
+        w16, _ = bf16_weight(w)
+        y, _, pre = gemm_bf16(a, w16, bias, taps_pad=taps_pad, act="silu", residual=residual, want_pre="fp32",
+                              dropout_p=dropout_p, seed=seed)
+        return pre, y
+    pre = gemm(a, w, bias, taps_pad=taps_pad)
+    return pre, affine_act(pre, None, None, "silu", residual, dropout_p=dropout_p, seed=seed)
 
 
 def split_small(x):
@@ -405,7 +490,7 @@ def _gemm_tc(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask,
                              float(alpha), _p(residual), N, _p(row_mask), _p(c), N,
                              _p(ln[0]) if fuse_ln else None, _p(ln[1]) if fuse_ln else None, float(ln[2]) if fuse_ln else 0.0,
                              _p(ln_out), _p(ln2[0]) if ln2_out is not None else None, _p(ln2[1]) if ln2_out is not None else None,
-                             _p(ln2_out), float(dropout_p), int(seed), 3 if PRECISION == "tf32x3" else 1,
+                             _p(ln2_out), float(dropout_p), int(seed), 1 if PRECISION == "tf32" else 3,
                              _p(w_small) if (w_small is not None and PRECISION == "tf32x3") else None, _stream()), "fs2k_gemm_tc")
     _count()
     if ln is None:
@@ -446,6 +531,58 @@ def _gemm_f32(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act
 # ---------------------------------------------------------------------------------------------
 # bf16 arithmetic mode (gemm_bf16.cu / gemm_wgrad_bf16.cu)
 # ---------------------------------------------------------------------------------------------
+_bf16_shadows: list = []   # weak references to FusedAdamW instances that keep a bf16 copy of their flat parameter buffer
+_bf16_cache: dict = {}
+
+
+def register_bf16_shadow(optimizer) -> None:
+    _bf16_shadows[:] = [r for r in _bf16_shadows if r() is not None and r() is not optimizer]
+    _bf16_shadows.append(weakref.ref(optimizer))
+
+
+def refresh_bf16_shadows(parameters=None) -> None:
+    """Once per model forward in the bf16 mode: re-sync the optimizers' bf16 weight shadows if anything but the update
+    kernel wrote the parameters since.  `parameters` (an iterable of the model's parameters) creates the shadow of the
+    optimizer that owns them on first use."""
+    if parameters is not None:
+        first = next(iter(parameters), None)
+        owner = getattr(first, "_fs2k_flat_owner", None) if first is not None else None
+        owner = owner() if owner is not None else None
+        if owner is not None:
+            owner.bf16_shadow()
+            return
+    for r in _bf16_shadows:
+        opt = r()
+        if opt is not None:
+            opt.bf16_shadow()
+
+
+def bf16_weight(w: torch.Tensor, want_lo: bool = False):
+    """(hi, lo) bf16 operands of an fp32 weight tensor: a view of the owning optimizer's shadow buffer when there is one
+    (zero launches), else a cast cached per weight version (static weights: synthesis / validation), else a cast."""
+    ptr = w.data_ptr()
+    if not want_lo:
+        for r in _bf16_shadows:
+            opt = r()
+            if opt is None or opt.flat_p16 is None:
+                continue
+            base = opt.flat_p.data_ptr()
+            if base <= ptr < base + 4 * opt.flat_p.numel() and w.is_contiguous():
+                off = (ptr - base) // 4
+                return opt.flat_p16[off: off + w.numel()].view(w.shape), None
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (ptr, w._version, tuple(w.shape), want_lo)
+    hit = None if capturing else _bf16_cache.get(ptr)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    hi, lo = cast_bf16(w, want_lo)
+    if not capturing:
+        if len(_bf16_cache) > 256:
+            _bf16_cache.clear()
+        _bf16_cache[ptr] = (key, hi, lo, w)  # holding w keeps its address from being reused while the entry lives
+    return hi, lo
+
+
 def cast_bf16(x, want_lo: bool = False):
     """fp32 → (hi = bf16(x), lo = bf16(x − hi) or None)."""
     x = _f32(x, "x")
@@ -854,6 +991,10 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=Non
     else:
         B, L = g.shape[0], g.shape[1]
     N, K = g.shape[-1], x.shape[-1]
+    if PRECISION == "bf16":
+        out = gemm_wgrad_bf16(g, x, taps, pad, conv_layout, accumulate_into)
+        if out is not None:
+            return out
     if PRECISION != "fp32" and B * L > 0 and lib().fs2k_gemm_wgrad_tc_supported(N, K, N, K):
         # tensor cores (tcgen05, MN-major operands); the kernel writes the parameter layout directly
         ws_bytes = lib().fs2k_gemm_wgrad_tc_workspace_bytes(B, L, N, K, taps)
@@ -861,7 +1002,7 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=Non
         acc = accumulate_into is not None and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
         out = accumulate_into if acc else torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
         assert out.numel() == N * K * taps
-        check(lib().fs2k_gemm_wgrad_tc(_p(g), N, _p(x), K, B, L, N, K, taps, pad, 3 if PRECISION == "tf32x3" else 1,
+        check(lib().fs2k_gemm_wgrad_tc(_p(g), N, _p(x), K, B, L, N, K, taps, pad, 1 if PRECISION == "tf32" else 3,
                                        _p(ws), ws_bytes, _p(out), int(acc), _stream()), "fs2k_gemm_wgrad_tc")
         _count(2)
         if accumulate_into is not None and not acc:

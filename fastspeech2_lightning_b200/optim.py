@@ -8,6 +8,8 @@ hyper-parameters as the reference's `torch.optim.AdamW` (fs2/model.py:530-537) w
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -38,12 +40,17 @@ class FusedAdamW(torch.optim.Optimizer):
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # bf16 shadow of the parameters (bf16 arithmetic mode): the update kernel writes it next to the fp32 masters,
+        # so the GEMMs' weight operands need no cast pass; created on first use (ops.bf16_weight)
+        self.flat_p16 = None
+        self._p16_sig = -1  # Σ parameter version counters at the last sync
         with torch.no_grad():
             for p, o in zip(params, offs):
                 view = self.flat_p[o: o + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_g[o: o + p.numel()].view_as(p)
+                p._fs2k_flat_owner = weakref.ref(self)
         self._params, self._offs, self.numel = params, offs, n
         self._step = 0
         # device copies of the per-step scalars {lr, 1−β1^t, sqrt(1−β2^t)} and the dropout seed base: a captured
@@ -98,7 +105,7 @@ class FusedAdamW(torch.optim.Optimizer):
             check(lib().fs2k_adamw_step_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
                                             self.flat_p.numel(), self.step_state.data_ptr(), float(g["betas"][0]), float(g["betas"][1]),
                                             float(g["eps"]), float(g["weight_decay"]), float(self.max_grad_norm or 0.0), 1.0 / world,
-                                            sumsq, stream), "fs2k_adamw_step_dev")
+                                            sumsq, self._p16_ptr(), stream), "fs2k_adamw_step_dev")
             ops._count()
             return loss
         self._step += 1
@@ -109,10 +116,40 @@ class FusedAdamW(torch.optim.Optimizer):
             sumsq = self._sumsq.data_ptr()
         check(lib().fs2k_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
                                     self.flat_p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                    float(g["weight_decay"]), self._step, float(self.max_grad_norm or 0.0), 1.0 / world, sumsq, stream),
+                                    float(g["weight_decay"]), self._step, float(self.max_grad_norm or 0.0), 1.0 / world, sumsq,
+                                    self._p16_ptr(), stream),
               "fs2k_adamw_step")
         ops._count()
+        self._mark_p16_synced()
         return loss
+
+    # ---- bf16 shadow of the weights ----------------------------------------------------------------------------------
+    def _p16_ptr(self):
+        return None if self.flat_p16 is None else self.flat_p16.data_ptr()
+
+    def _mark_p16_synced(self) -> None:
+        """Called right after _bump_versions (every counter + 1) when the update kernel also wrote the shadow."""
+        if self.flat_p16 is not None and self._p16_sig >= 0:
+            self._p16_sig += len(self._params)
+
+    def _version_sig(self) -> int:
+        return sum(p._version for p in self._params)
+
+    def bf16_shadow(self) -> torch.Tensor:
+        """bf16 copy of the flat parameter buffer, kept current by the update kernel.  Anything else that writes the
+        parameters (load_state_dict, an in-place fill) bumps their version counters: one cast launch re-syncs.  Called once
+        per model forward (ops.refresh_bf16_shadows), not per weight."""
+        if self.flat_p16 is None:
+            self.flat_p16 = torch.empty(self.flat_p.numel(), dtype=torch.bfloat16, device=self.flat_p.device)
+            ops.register_bf16_shadow(self)
+        if not torch.cuda.is_current_stream_capturing():
+            sig = self._version_sig()
+            if sig != self._p16_sig:
+                check(lib().fs2k_cast_bf16(self.flat_p.data_ptr(), self.flat_p.numel(), self.flat_p16.data_ptr(), None,
+                                           torch.cuda.current_stream().cuda_stream), "fs2k_cast_bf16")
+                ops._count()
+                self._p16_sig = sig
+        return self.flat_p16
 
 
     def begin_graph_step(self) -> None:
@@ -121,6 +158,7 @@ class FusedAdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         self._bump_versions()
+        self._mark_p16_synced()  # the replayed update kernel writes the bf16 shadow too
         self._opt_called = True  # LRScheduler's "scheduler.step() before optimizer.step()" check
         b1, b2 = g["betas"]
         seed = int(torch.randint(0, 2**62, (1,)).item())

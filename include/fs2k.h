@@ -319,18 +319,19 @@ int fs2k_trim_transpose(const float* mel, const int* lens, const long long* out_
 /* ---- optimizer over one flat buffer (torch.optim.AdamW at fs2/model.py:530-537; clip 1.0 at fs2/cli/train.py:38) ---
  * sumsq: out[0] = Σ g² (fp64).  adamw_step: g' = g·grad_scale·min(1, max_norm/(‖g·grad_scale‖+1e-6)) when sumsq is given
  * (grad_scale = 1/world_size folds the data-parallel mean), then AdamW with decoupled weight decay and bias correction
- * for `step` (1-based). */
+ * for `step` (1-based).  p_bf16 (optional): bf16 shadow of the updated parameters, written by the same launch — the
+ * weight operands of the bf16 arithmetic mode. */
 int fs2k_sumsq(const float* g, long N, double* out, fs2k_stream_t stream);
 int fs2k_adamw_step(float* p, const float* g, float* m, float* v, long N, float lr, float beta1, float beta2, float eps,
                     float weight_decay, long step, float max_norm, float grad_scale, const double* sumsq,
-                    fs2k_stream_t stream);
+                    void* p_bf16, fs2k_stream_t stream);
 /* CUDA-graph replay of a whole training step: per-step scalars live in device memory so that a captured launch
  * sees fresh values.  step_state = 4 floats {lr, 1−β1^t, sqrt(1−β2^t), unused}; set_step_state writes them and the
  * dropout seed base in one tiny launch (by-value kernel arguments, so no host staging buffer can race).
  * set_dropout_seed_base registers the device counter every dropout kernel adds to its seed (NULL = none). */
 int fs2k_adamw_step_dev(float* p, const float* g, float* m, float* v, long N, const float* step_state, float beta1,
                         float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
-                        const double* sumsq, fs2k_stream_t stream);
+                        const double* sumsq, void* p_bf16, fs2k_stream_t stream);
 int fs2k_set_step_state(float* step_state, unsigned long long* seed_base, float lr, float bias_correction1,
                         float bias_correction2_sqrt, long seed_base_value, fs2k_stream_t stream);
 int fs2k_set_dropout_seed_base(const unsigned long long* device_counter);
