@@ -36,6 +36,10 @@ WORKLOADS = {
 }
 
 
+DTYPES = {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor cores)",
+          "bf16": "bf16 (tcgen05 kind::f16 operands; fp32 accumulate, residual stream, norms, softmax, master weights)"}
+
+
 def flops_fwd(B, T, F, aligner=False):
     """forward FLOPs on the padded B×L rectangle."""
     f = 4 * T * (3_019_264 + 1024 * T) + 4 * F * (3_019_264 + 1024 * F) + 3 * T * 663_552 + F * 40_960 + F * 8_683_520
@@ -152,6 +156,13 @@ def kernel_work(name, args):
     """(flops, bytes) of one C-ABI call, from its arguments (DESIGN.md lists the formulas)."""
     if name == "fs2k_gemm_f32" or name == "fs2k_gemm_tc":
         B, L, K, N, taps = args[2], args[3], args[4], args[6], args[7]
+        return 2.0 * B * L * K * N * taps, 4.0 * (B * L * (K + N) + N * K * taps)
+    if name == "fs2k_gemm_bf16":
+        a16, B, L, K, N, taps = args[1], args[3], args[4], args[5], args[9], args[10]
+        out_b = (4 if args[20] else 0) + (2 if args[22] else 0) + (4 if args[24] else 0) + (2 if args[25] else 0) + (4 if args[17] else 0)
+        return 2.0 * B * L * K * N * taps, B * L * (K * (2 if a16 else 4) + N * out_b) + 2.0 * N * K * taps
+    if name == "fs2k_gemm_wgrad_bf16":
+        B, L, N, K, taps = args[4], args[5], args[6], args[7], args[8]
         return 2.0 * B * L * K * N * taps, 4.0 * (B * L * (K + N) + N * K * taps)
     if name == "fs2k_attention_f32":
         B, L, H, hd = args[2], args[3], args[4], args[5]
@@ -273,7 +284,7 @@ def run_ours(args, wl_name, wl, rank, world, device):
     line = {
         "metric": wl["metric"], "value": all_frames / (ms_dev * 1e-3), "unit": wl["unit"], "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor cores)"}[ops.PRECISION], "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[ops.PRECISION], "data": "synthetic",
         "config": {"workload": f"{wl_name}: base config random init, teacher-forced synthesis forward, B={B}/GPU, T<={T}, F<={F}, 80-bin mel",
                    "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "parallelism": f"replicas x{world}, no collectives", "launch": "eager" if args.eager else "cuda graph replay"},
         "e2e": {"value": all_frames / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
@@ -404,7 +415,7 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
     line = {
         "metric": wl["metric"], "value": utts / (ms_dev * 1e-3), "unit": wl["unit"], "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor cores)"}[ops.PRECISION],
+        "vs_baseline": None, "dtype": DTYPES[ops.PRECISION],
         "data": "synthetic",
         "config": {"workload": f"{wl_name}: base config random init, training step with learned alignment (aligner+MAS, "
                                f"duration/pitch/energy/mel/postnet/CTC/bin losses, backward, clip 1.0, AdamW+Noam), B={B}/GPU, T<={T}, F<={F}",
@@ -604,8 +615,8 @@ def main():
     ap.add_argument("--also", default="synth_c1,synth_c1@dec-tf32,mas_c2", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
-    ap.add_argument("--backward-precision", default=None, choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3", "bf16"])
+    ap.add_argument("--backward-precision", default=None, choices=["fp32", "tf32", "tf32x3", "bf16"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
