@@ -96,6 +96,29 @@ def attention(qkv, lengths, heads: int, dropout: float = 0.0, order=None):
     return ops.attention(qkv, lengths, heads, order=order)
 
 
+def qkv_attention(x, in_proj_weight, in_proj_bias, lengths, heads: int, dropout: float = 0.0, order=None):
+    """MultiheadAttention's in-projection + masked scaled-dot-product attention (torchaudio conformer.py:193-202).
+    bf16 mode (head_dim 128): one bf16 qkv tensor from the GEMM epilogue feeds the tcgen05 attention kernels;
+    other modes: the fp32 GEMM followed by the fp32 attention kernel."""
+    D = x.shape[-1]
+    if (ops.PRECISION == "bf16" and D // heads == 128 and lib_supports_bf16_linear(D, in_proj_weight.shape[0])):
+        if _needs_grad(x, in_proj_weight, in_proj_bias) or dropout > 0.0:
+            from . import autograd_fns as fns
+
+            return fns.qkv_attention_bf16(x, in_proj_weight, in_proj_bias, lengths, heads, dropout, order)
+        w16, _ = ops.bf16_weight(in_proj_weight.detach())
+        _, qkv16, _ = ops.gemm_bf16(x, w16, in_proj_bias, want_c=False, want_c16=True)
+        return ops.attention_bf16(qkv16, lengths, heads, order=order)
+    qkv = linear(x, in_proj_weight, in_proj_bias)
+    return attention(qkv, lengths, heads, dropout=dropout, order=order)
+
+
+def lib_supports_bf16_linear(K: int, N: int) -> bool:
+    from ._lib import lib
+
+    return bool(lib().fs2k_gemm_bf16_supported(K, N, K, 1, 0, 0))
+
+
 def rowdot(x, weight, bias, mask):
     """nn.Linear(D→1) + squeeze(-1) + ·mask (fs2/variance_adaptor.py:58-61)."""
     if _needs_grad(x, weight, bias):

@@ -337,6 +337,40 @@ def attention(qkv, lengths, heads, dropout_p=0.0, order=None):
     return _Attention.apply(qkv.contiguous(), lengths, heads, float(dropout_p), order)
 
 
+class _QkvAttention(torch.autograd.Function):
+    """bf16 mode: in-projection GEMM (bf16 qkv straight from its epilogue) + tensor-core attention as one node —
+    the fp32 qkv tensor never exists (torchaudio conformer.py:193-202 / nn.MultiheadAttention's in_proj + SDPA)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lengths, heads, dropout_p, order):
+        seed = _seed(dropout_p)
+        w16, _ = ops.bf16_weight(weight.detach())
+        _, qkv16, _ = ops.gemm_bf16(x, w16, bias.detach() if bias is not None else None, want_c=False, want_c16=True)
+        out, lse = ops.attention_bf16(qkv16, lengths, heads, want_lse=True, dropout_p=dropout_p, seed=seed, order=order)
+        ctx.save_for_backward(x, qkv16, out, lse, lengths)
+        ctx.meta = (heads, dropout_p, seed, bias is not None)
+        ctx.order = order
+        ctx.params = (weight, bias)
+        ctx.precision = ops.PRECISION
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, qkv16, out, lse, lengths = ctx.saved_tensors
+        heads, p, seed, has_bias = ctx.meta
+        weight, bias = ctx.params
+        dqkv = ops.attention_bwd_bf16(qkv16, out, lse, g.contiguous(), lengths, heads, p, seed, ctx.order)
+        w_taps = weight.detach().reshape(1, *weight.shape)
+        dx, dw, db = _gemm_backward(dqkv, x, w_taps, 0, False, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    has_bias and ctx.needs_input_grad[2], weight, bias, wt=None, precision=ctx.precision)
+        return dx, dw, db, None, None, None, None
+
+
+def qkv_attention_bf16(x, weight, bias, lengths, heads, dropout_p=0.0, order=None):
+    return _QkvAttention.apply(x.contiguous(), weight, bias, lengths, heads, float(dropout_p), order)
+
+
 class _Rowdot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mask):

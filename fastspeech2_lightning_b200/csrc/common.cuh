@@ -116,12 +116,14 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // counter-based uniform in [0,1): splitmix64 finaliser of (seed, index).  Dropout masks are regenerated
 // from the seed in the backward pass instead of being stored.
-__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long i) {
+__device__ __forceinline__ unsigned long long hash_u64(unsigned long long seed, unsigned long long i) {
     unsigned long long z = seed * 0x9E3779B97F4A7C15ull + i + 0x632BE59BD9B4E019ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(z >> 40) * (1.0f / 16777216.0f);
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long i) {
+    return (float)(hash_u64(seed, i) >> 40) * (1.0f / 16777216.0f);
 }
 // Dropout under CUDA-graph replay: the by-value seeds of a captured launch are frozen, so every dropout kernel
 // adds *g_seed_base (a device counter the host rewrites before each replay; null → 0) to its seed on entry.

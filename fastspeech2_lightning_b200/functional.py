@@ -29,8 +29,8 @@ def conformer_layer(x, lengths, layer, training: bool, order=None):
     # self-attention block (:191-203)
     ln = ag.layernorm(x, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, layer.self_attn_layer_norm.eps)
     mha = layer.self_attn
-    qkv = ag.linear(ln, mha.in_proj_weight, mha.in_proj_bias)
-    o = ag.attention(qkv, lengths, layer.num_heads, dropout=mha.dropout if training else 0.0, order=order)
+    o = ag.qkv_attention(ln, mha.in_proj_weight, mha.in_proj_bias, lengths, layer.num_heads,
+                         dropout=mha.dropout if training else 0.0, order=order)
     x = ag.linear(o, mha.out_proj.weight, mha.out_proj.bias, residual=x, dropout=p if training else 0.0)
     # convolution module (:42-75, :168-174)
     cm = layer.conv_module

@@ -703,6 +703,34 @@ def attention(qkv, lens, heads: int, want_lse: bool = False, dropout_p: float = 
     return (out, lse) if want_lse else out
 
 
+def attention_bf16(qkv16, lens, heads: int, want_lse: bool = False, dropout_p: float = 0.0, seed: int = 0, order=None):
+    """Tensor-core attention of the bf16 mode: qkv16 [B,L,3D] bf16 → out [B,L,D] fp32 (+ lse [B,H,L])."""
+    assert qkv16.is_cuda and qkv16.dtype == torch.bfloat16 and qkv16.is_contiguous()
+    lens = _i32(lens, "lens")
+    B, L, D3 = qkv16.shape
+    D = D3 // 3
+    out = torch.empty((B, L, D), dtype=torch.float32, device=qkv16.device)
+    lse = torch.empty((B, heads, L), dtype=torch.float32, device=qkv16.device) if want_lse else None
+    check(lib().fs2k_attention_bf16(_p(qkv16), _p(lens), B, L, heads, D // heads, float(dropout_p), int(seed), _p(out), _p(lse), _p(order), _stream()),
+          "fs2k_attention_bf16")
+    _count()
+    return (out, lse) if want_lse else out
+
+
+def attention_bwd_bf16(qkv16, out, lse, dout, lens, heads: int, dropout_p: float = 0.0, seed: int = 0, order=None):
+    assert qkv16.dtype == torch.bfloat16 and qkv16.is_contiguous()
+    out, dout = _f32(out, "out"), _f32(dout, "dout")
+    B, L, D3 = qkv16.shape
+    D = D3 // 3
+    dout16, _ = cast_bf16(dout)
+    delta = torch.empty((B, heads, L), dtype=torch.float32, device=qkv16.device)
+    dqkv = torch.empty((B, L, D3), dtype=torch.float32, device=qkv16.device)
+    check(lib().fs2k_attention_bwd_bf16(_p(qkv16), _p(out), _p(lse), _p(dout), _p(dout16), _p(_i32(lens)), B, L, heads, D // heads,
+                                        float(dropout_p), int(seed), _p(delta), _p(dqkv), _p(order), _stream()), "fs2k_attention_bwd_bf16")
+    _count(3)
+    return dqkv
+
+
 def dwconv(x, weight, bias, *, channels: int, glu: bool = False, scale=None, shift=None):
     """x [B,L,ldx] → [B,L,channels]; weight [C,1,K]."""
     x = _f32(x, "x")

