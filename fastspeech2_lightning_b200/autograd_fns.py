@@ -784,5 +784,25 @@ def gst_token_attention(q, k, v, heads):
     return _GstTokenAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(), heads)
 
 
+class _Tanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.tanh(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return ops.act_bwd(g.contiguous(), y, "tanh")
+
+
+def tanh(x):
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _Tanh.apply(x.contiguous())
+    return ops.tanh(x.detach())
+
+
 def tanh_row(table, index):
     return ops.tanh(table.detach()[index: index + 1].contiguous())

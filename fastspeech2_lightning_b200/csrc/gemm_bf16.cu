@@ -28,6 +28,7 @@ constexpr int HB_THREADS = 256;
 constexpr int HB_WARPS = HB_THREADS / 32;
 constexpr int HB_MAX_STAGES = 8;
 constexpr int HB_CONV_THREADS = 128;  // warps 4..7 convert the fp32 A tile
+constexpr int HB_ROWS = 2;            // rows a warp keeps in flight in the store pass
 
 struct HbEpilogue {
     const float* bias; const float* scale; const float* shift;
@@ -208,39 +209,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         const int act = ep.act;
         const float alpha = ep.alpha;
-        for (int r = warp; r < rows_valid; r += HB_WARPS) {
-            const long m = (long)b_idx * L + l0 + r;
-            float4 res[2];
+        // HB_ROWS rows per warp trip: every global read of the group (residual, row mask) is issued before any is used
+        for (int rb = warp; rb < rows_valid; rb += HB_WARPS * HB_ROWS) {
+            float4 res[HB_ROWS][2];
+            float rm[HB_ROWS];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                res[j] = zero4;
-                if (has[j] && ep.residual)
-                    res[j] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n0 + (lane + 32 * j) * 4);
-            }
-            const float rm = ep.row_mask ? (ep.row_mask[m] ? 1.f : 0.f) : 1.f;
+            for (int u = 0; u < HB_ROWS; ++u) {
+                const int r = rb + u * HB_WARPS;
+                const long m = (long)b_idx * L + l0 + r;
+                rm[u] = 1.f;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (!has[j]) continue;
-                const int qv = lane + 32 * j;
-                float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
-                v.x += bias4[j].x; v.y += bias4[j].y; v.z += bias4[j].z; v.w += bias4[j].w;
-                if (ep.P32) *reinterpret_cast<float4*>(ep.P32 + (size_t)m * ep.ldp + n0 + qv * 4) = v;
-                if (ep.P16) *reinterpret_cast<uint2*>(ep.P16 + (size_t)m * ep.ldp + n0 + qv * 4) = hb_pack4(v);
-                v.x = hb_act(v.x * sc4[j].x + sh4[j].x, act) * alpha;
-                v.y = hb_act(v.y * sc4[j].y + sh4[j].y, act) * alpha;
-                v.z = hb_act(v.z * sc4[j].z + sh4[j].z, act) * alpha;
-                v.w = hb_act(v.w * sc4[j].w + sh4[j].w, act) * alpha;
-                if (DROPOUT) {
-                    const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
-                    v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
-                    v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
-                    v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
-                    v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                for (int j = 0; j < 2; ++j) {
+                    res[u][j] = zero4;
+                    if (r < rows_valid && has[j] && ep.residual)
+                        res[u][j] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n0 + (lane + 32 * j) * 4);
                 }
-                v.x = (v.x + res[j].x) * rm; v.y = (v.y + res[j].y) * rm;
-                v.z = (v.z + res[j].z) * rm; v.w = (v.w + res[j].w) * rm;
-                if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
-                if (ep.C16) *reinterpret_cast<uint2*>(ep.C16 + (size_t)m * ep.ldc16 + n0 + qv * 4) = hb_pack4(v);
+                if (r < rows_valid && ep.row_mask) rm[u] = ep.row_mask[m] ? 1.f : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < HB_ROWS; ++u) {
+                const int r = rb + u * HB_WARPS;
+                if (r >= rows_valid) break;  // warp-uniform
+                const long m = (long)b_idx * L + l0 + r;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (!has[j]) continue;
+                    const int qv = lane + 32 * j;
+                    float4 v = *reinterpret_cast<const float4*>(stag + (size_t)r * pitch + qv * 4);
+                    v.x += bias4[j].x; v.y += bias4[j].y; v.z += bias4[j].z; v.w += bias4[j].w;
+                    if (ep.P32) *reinterpret_cast<float4*>(ep.P32 + (size_t)m * ep.ldp + n0 + qv * 4) = v;
+                    if (ep.P16) *reinterpret_cast<uint2*>(ep.P16 + (size_t)m * ep.ldp + n0 + qv * 4) = hb_pack4(v);
+                    v.x = hb_act(v.x * sc4[j].x + sh4[j].x, act) * alpha;
+                    v.y = hb_act(v.y * sc4[j].y + sh4[j].y, act) * alpha;
+                    v.z = hb_act(v.z * sc4[j].z + sh4[j].z, act) * alpha;
+                    v.w = hb_act(v.w * sc4[j].w + sh4[j].w, act) * alpha;
+                    if (DROPOUT) {
+                        const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
+                        v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
+                        v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
+                        v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
+                        v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                    }
+                    v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
+                    v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];
+                    if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + n0 + qv * 4) = v;
+                    if (ep.C16) *reinterpret_cast<uint2*>(ep.C16 + (size_t)m * ep.ldc16 + n0 + qv * 4) = hb_pack4(v);
+                }
             }
         }
     }

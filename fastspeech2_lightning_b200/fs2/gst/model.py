@@ -7,10 +7,9 @@
   attention) runs on libfs2k kernels (csrc/gst.cu): synthesis / validation with
   folded BatchNorm in one fused conv kernel; training through autograd Functions over the raw conv, the
   BatchNorm batch-statistics kernels, conv dgrad / wgrad, a GRU with back-propagation through time and
-  the token-attention backward (`TRAINING_KERNELS = False` selects torch's cuDNN / ATen path instead,
-  which CPU tensors always take).
+  the token-attention backward.  There is no library (cuDNN / ATen) path and no CPU path: the torch layers below
+  are parameter containers whose own forward is never called.
 """
-import math
 from collections.abc import Sequence
 
 import torch
@@ -19,15 +18,16 @@ from ... import autograd as ag
 from ... import ops
 
 
-# Training through the reference encoder / token layer on libfs2k kernels (autograd Functions over the conv / BatchNorm /
-# GRU / attention kernels).  False = torch autograd over cuDNN / ATen library calls.
-TRAINING_KERNELS = True
-
-
-def _kernel_path(module, *tensors) -> bool:
-    """Kernels serve the no-gradient eval case; anything that needs autograd or batch statistics takes the library path."""
+def _fused_eval_path(module, *tensors) -> bool:
+    """No gradient and eval mode: the fused kernels with folded BatchNorm; otherwise the autograd Functions over the
+    training kernels (batch statistics, dgrad / wgrad, BPTT)."""
     return (not module.training) and not (torch.is_grad_enabled() and (
         any(t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters())))
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{what} must be a CUDA tensor: the GST modules run on libfs2k kernels only (no CPU / library path)")
 
 
 class MultiHeadedAttention(torch.nn.Module):
@@ -43,15 +43,7 @@ class MultiHeadedAttention(torch.nn.Module):
         self.dropout = torch.nn.Dropout(p=dropout_rate)
 
     def forward(self, query, key, value, mask=None):
-        """LIBRARY path (see module docstring): gst/attn.py:172-194."""
-        B = query.size(0)
-        q = self.linear_q(query).view(B, -1, self.h, self.d_k).transpose(1, 2)
-        k = self.linear_k(key).view(B, -1, self.h, self.d_k).transpose(1, 2)
-        v = self.linear_v(value).view(B, -1, self.h, self.d_k).transpose(1, 2)
-        scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(self.d_k)
-        attn = torch.softmax(scores, dim=-1)
-        x = torch.matmul(self.dropout(attn), v).transpose(1, 2).contiguous().view(B, -1, self.h * self.d_k)
-        return self.linear_out(x)
+        raise RuntimeError("parameter container of gst/attn.py:96-194: StyleTokenLayer.forward runs the kernels")
 
 
 class ReferenceEncoder(torch.nn.Module):
@@ -80,7 +72,8 @@ class ReferenceEncoder(torch.nn.Module):
 
     def forward(self, speech: torch.Tensor) -> torch.Tensor:
         """gst/model.py:179-199.  CUDA inputs run on libfs2k kernels (fused eval path or autograd Functions)."""
-        if _kernel_path(self, speech):
+        _require_cuda(speech, "speech")
+        if _fused_eval_path(self, speech):
             x = speech.detach().contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
             n = len(self.convs) // 3
             for i in range(n):
@@ -92,20 +85,14 @@ class ReferenceEncoder(torch.nn.Module):
             g = self.gru
             return ops.gru_last_hidden(hs, g.weight_ih_l0.detach(), g.weight_hh_l0.detach(), g.bias_ih_l0.detach(),
                                        g.bias_hh_l0.detach())
-        if TRAINING_KERNELS and speech.is_cuda:
-            from ... import autograd_fns as fns
+        from ... import autograd_fns as fns
 
-            x = speech.contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
-            n = len(self.convs) // 3
-            for i in range(n):
-                x = fns.conv2d_s2_bn_relu(x, self.convs[3 * i], self.convs[3 * i + 1], self.training)
-            hs = x.permute(0, 1, 3, 2).reshape(x.shape[0], x.shape[1], -1)  # [B,T',W',C] → [B,T',C·W'] (:195-197)
-            return fns.gru_last_hidden(hs, self.gru)
-        batch_size = speech.size(0)
-        hs = self.convs(speech.unsqueeze(1)).transpose(1, 2)
-        hs = hs.contiguous().view(batch_size, hs.size(1), -1)
-        _, ref_embs = self.gru(hs)
-        return ref_embs[-1]
+        x = speech.contiguous().unsqueeze(-1)  # channels-last image [B, F, n_mels, 1]
+        n = len(self.convs) // 3
+        for i in range(n):
+            x = fns.conv2d_s2_bn_relu(x, self.convs[3 * i], self.convs[3 * i + 1], self.training)
+        hs = x.permute(0, 1, 3, 2).reshape(x.shape[0], x.shape[1], -1)  # [B,T',W',C] → [B,T',C·W'] (:195-197)
+        return fns.gru_last_hidden(hs, self.gru)
 
 
 class StyleTokenLayer(torch.nn.Module):
@@ -118,7 +105,8 @@ class StyleTokenLayer(torch.nn.Module):
                                         dropout_rate=dropout_rate)
 
     def forward(self, ref_embs: torch.Tensor) -> torch.Tensor:
-        if _kernel_path(self, ref_embs):
+        _require_cuda(ref_embs, "ref_embs")
+        if _fused_eval_path(self, ref_embs):
             m = self.mha
             tokens = ops.tanh(self.gst_embs.detach())
             q = ops.gemm(ref_embs.detach().contiguous(), m.linear_q.weight.detach(), m.linear_q.bias.detach())
@@ -126,19 +114,15 @@ class StyleTokenLayer(torch.nn.Module):
             v = ops.gemm(tokens, m.linear_v.weight.detach(), m.linear_v.bias.detach())
             o = ops.gst_token_attention(q, k, v, m.h)
             return ops.gemm(o, m.linear_out.weight.detach(), m.linear_out.bias.detach())
-        if TRAINING_KERNELS and ref_embs.is_cuda:
-            from ... import autograd_fns as fns
+        from ... import autograd_fns as fns
 
-            m = self.mha
-            tokens = torch.tanh(self.gst_embs)
-            q = fns.linear(ref_embs, m.linear_q.weight, m.linear_q.bias, None, 1.0, None)
-            k = fns.linear(tokens, m.linear_k.weight, m.linear_k.bias, None, 1.0, None)
-            v = fns.linear(tokens, m.linear_v.weight, m.linear_v.bias, None, 1.0, None)
-            o = fns.gst_token_attention(q, k, v, m.h)
-            return fns.linear(o, m.linear_out.weight, m.linear_out.bias, None, 1.0, None)
-        batch_size = ref_embs.size(0)
-        gst_embs = torch.tanh(self.gst_embs).unsqueeze(0).expand(batch_size, -1, -1)
-        return self.mha(ref_embs.unsqueeze(1), gst_embs, gst_embs, None).squeeze(1)
+        m = self.mha
+        tokens = fns.tanh(self.gst_embs)
+        q = fns.linear(ref_embs, m.linear_q.weight, m.linear_q.bias, None, 1.0, None)
+        k = fns.linear(tokens, m.linear_k.weight, m.linear_k.bias, None, 1.0, None)
+        v = fns.linear(tokens, m.linear_v.weight, m.linear_v.bias, None, 1.0, None)
+        o = fns.gst_token_attention(q, k, v, m.h)
+        return fns.linear(o, m.linear_out.weight, m.linear_out.bias, None, 1.0, None)
 
 
 class StyleEncoder(torch.nn.Module):

@@ -64,3 +64,24 @@ def case_state_dict(meta):
 
 def lookup(n, prefix):
     return {f"{prefix}{i}": i for i in range(n)}
+
+
+def gst_reference_forward(enc, speech):
+    """Plain-torch statement of the reference StyleEncoder.forward (gst/model.py:87-100,179-199,241-257; gst/attn.py:172-194)
+    over the parameter-holding torch layers of our module (any dtype / device torch supports) — the checker of the GST
+    kernels; the product module itself has no library path."""
+    import math
+
+    B = speech.size(0)
+    hs = enc.ref_enc.convs(speech.unsqueeze(1)).transpose(1, 2)
+    hs = hs.contiguous().view(B, hs.size(1), -1)
+    _, ref_embs = enc.ref_enc.gru(hs)
+    ref = ref_embs[-1]
+    m = enc.stl.mha
+    tokens = torch.tanh(enc.stl.gst_embs).unsqueeze(0).expand(B, -1, -1)
+    q = m.linear_q(ref.unsqueeze(1)).view(B, -1, m.h, m.d_k).transpose(1, 2)
+    k = m.linear_k(tokens).view(B, -1, m.h, m.d_k).transpose(1, 2)
+    v = m.linear_v(tokens).view(B, -1, m.h, m.d_k).transpose(1, 2)
+    attn = torch.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(m.d_k), dim=-1)
+    x = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, -1, m.h * m.d_k)
+    return m.linear_out(x).squeeze(1)
