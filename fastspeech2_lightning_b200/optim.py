@@ -108,6 +108,7 @@ class FusedAdamW(torch.optim.Optimizer):
                                             sumsq, self._p16_ptr(), stream), "fs2k_adamw_step_dev")
             ops._count()
             return loss
+        self._adopt_foreign_grads()
         self._step += 1
         self._bump_versions()
         if self.max_grad_norm is not None:
@@ -122,6 +123,59 @@ class FusedAdamW(torch.optim.Optimizer):
         ops._count()
         self._mark_p16_synced()
         return loss
+
+    def _adopt_foreign_grads(self) -> None:
+        """The update reads the flat gradient buffer.  Anything that replaced a parameter's `.grad` (nn.Module.zero_grad /
+        a zero_grad hook with set_to_none, DDP's gradient_as_bucket_view, a hand-assigned tensor) made autograd accumulate
+        somewhere else: copy such gradients into their slice and re-point `.grad` at it.  A parameter whose grad is None
+        gets a zero slice — unlike torch.optim.AdamW, which skips it entirely, it still receives weight decay and moment
+        decay (every parameter of this model receives a gradient in every step, so the two only differ for frozen-by-hand
+        parameters, which should be excluded from the optimizer instead)."""
+        base = self.flat_g.data_ptr()
+        for p, o in zip(self._params, self._offs):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + 4 * o:
+                continue
+            view = self.flat_g[o: o + p.numel()].view_as(p)
+            if g is None:
+                view.zero_()
+            else:
+                view.copy_(g)
+            p.grad = view
+
+    # ---- checkpoint format: torch.optim.AdamW's (per-parameter step / exp_avg / exp_avg_sq) -----------------------------------
+    def state_dict(self):
+        """Same layout as the reference's torch.optim.AdamW (fs2/model.py:530-537), sliced out of the flat moment buffers,
+        so Lightning checkpoints (`optimizer_states`) are interchangeable in both directions."""
+        sd = super().state_dict()
+        state = {}
+        if self._step > 0:
+            for i, (p, o) in enumerate(zip(self._params, self._offs)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self._step)),
+                            "exp_avg": self.flat_m[o: o + n].view_as(p).clone(),
+                            "exp_avg_sq": self.flat_v[o: o + n].view_as(p).clone()}
+        sd["state"] = state
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        state = state_dict.get("state", {})
+        super().load_state_dict({"state": {}, "param_groups": state_dict["param_groups"]})
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        steps = set()
+        for i, (p, o) in enumerate(zip(self._params, self._offs)):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            n = p.numel()
+            self.flat_m[o: o + n].view_as(p).copy_(st["exp_avg"])
+            self.flat_v[o: o + n].view_as(p).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdamW keeps one step count for all parameters; the checkpoint has {sorted(steps)}")
+        self._step = steps.pop() if steps else 0
 
     # ---- bf16 shadow of the weights ----------------------------------------------------------------------------------
     def _p16_ptr(self):

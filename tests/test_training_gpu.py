@@ -294,3 +294,72 @@ def test_three_optimisation_steps_follow_the_oracle_with_torch_adamw():
     assert abs(want[2] - want[0]) > 1e-3 * abs(want[0]), "the steps did not change the loss: the test would prove nothing"
     for a, b in zip(got, want):
         assert abs(a - b) <= 2e-4 * abs(b), (got, want)
+
+
+def test_fused_adamw_checkpoint_is_interchangeable_with_torch_adamw():
+    """state_dict / load_state_dict in torch.optim.AdamW's layout: save after two steps, resume in a fresh FusedAdamW AND
+    in a torch AdamW, take a third step — all three trajectories agree (moments and bias-correction step restored)."""
+    from fastspeech2_lightning_b200.optim import FusedAdamW
+
+    g = torch.Generator().manual_seed(1)
+    shapes = [(64, 48), (48,), (16, 8, 3)]
+    kw = dict(lr=2e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
+    grads = [[torch.randn(s, generator=g).to(DEV) for s in shapes] for _ in range(3)]
+
+    def run(opt_cls, params, steps, **extra):
+        opt = opt_cls(params, **kw, **extra)
+        for gr in steps:
+            for p, x in zip(params, gr):
+                if p.grad is None:
+                    p.grad = x.clone()
+                else:
+                    p.grad.copy_(x)
+            opt.step()
+        return opt
+
+    init = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    a = [torch.nn.Parameter(t.clone()) for t in init]
+    opt_a = run(FusedAdamW, a, grads[:2])
+    sd = opt_a.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 2.0
+    # resume: ours from ours
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    opt_b = FusedAdamW(b, **kw)
+    opt_b.load_state_dict(sd)
+    # resume: torch AdamW from ours
+    c = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    opt_c = torch.optim.AdamW(c, **kw)
+    opt_c.load_state_dict(sd)
+    # and ours from torch's own state dict
+    d0 = [torch.nn.Parameter(t.clone()) for t in init]
+    opt_t = run(torch.optim.AdamW, d0, grads[:2])
+    d = [torch.nn.Parameter(p.detach().clone()) for p in d0]
+    opt_d = FusedAdamW(d, **kw)
+    opt_d.load_state_dict(opt_t.state_dict())
+    for params, opt in ((a, opt_a), (b, opt_b), (c, opt_c), (d, opt_d)):
+        for p, x in zip(params, grads[2]):
+            if p.grad is None:
+                p.grad = x.clone()
+            else:
+                p.grad.copy_(x)
+        opt.step()
+    for pa, pb, pc, pd in zip(a, b, c, d):
+        close(pb, pa, 1e-6, "FusedAdamW resumed from its own checkpoint")
+        close(pc, pa, 2e-6, "torch AdamW resumed from a FusedAdamW checkpoint")
+        close(pd, pa, 2e-6, "FusedAdamW resumed from a torch AdamW checkpoint")
+
+
+def test_fused_adamw_adopts_gradients_that_left_the_flat_buffer():
+    from fastspeech2_lightning_b200.optim import FusedAdamW
+
+    p = torch.nn.Parameter(torch.ones(40, 8, device=DEV))
+    r = torch.nn.Parameter(torch.ones(40, 8, device=DEV))
+    opt, ref = FusedAdamW([p], lr=1e-2), torch.optim.AdamW([r], lr=1e-2)
+    p.grad = None                      # what nn.Module.zero_grad(set_to_none=True) leaves behind
+    (p * 3.0).sum().backward()         # autograd allocates a fresh .grad outside the flat buffer
+    (r * 3.0).sum().backward()
+    assert p.grad.data_ptr() != opt.flat_g.data_ptr()
+    opt.step()
+    ref.step()
+    close(p, r, 1e-6, "step with a foreign .grad")
+    assert p.grad.data_ptr() == opt.flat_g.data_ptr()
