@@ -27,8 +27,17 @@ import torch  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[0]: base config, teacher-forced synthesis, B=16, T≈80 → F≈500
     "synth_c1": dict(kind="synth", batch=16, src=(60, 80), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
-    # configs[3]: 256 utterances of 20-200 phonemes in length-sorted batches of 32 (one step = one batch of 32)
-    "synth_c4": dict(kind="synth", batch=32, src=(20, 200), learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s"),
+    # configs[3]: 256 utterances of 20-200 phonemes (up to ~1500 frames), multispeaker + GST (400-frame style reference mel
+    # through the GST reference encoder), dealt to the ranks as length-sorted batches of 32 (parallel.shard_utterances);
+    # one step = one batch of 32, the timed steps cycle through the rank's batches
+    "synth_c4": dict(kind="synth", batch=32, src=(20, 200), n_utts=256, learn_alignment=False, metric="mel_frames_per_sec", unit="mel frames/s",
+                     model_kw=dict(multispeaker=True, use_global_style_token_module=True), n_speakers=8, style_frames=400,
+                     desc="multispeaker + GST (400-frame style mel → reference encoder), 256 utterances of 20-200 phonemes in length-sorted batches of 32"),
+    # configs[4]: long-utterance stress — one utterance of 1000 phonemes / ~8000 frames through the learned-alignment forward
+    # (aligner + MAS over the 8000 × 1000 matrix + both Conformers + PostNet), eval mode, no gradient
+    "synth_c5": dict(kind="synth", batch=1, src=(1000, 1000), learn_alignment=True, align_forward=True, dur_range=(6, 10),
+                     metric="mel_frames_per_sec", unit="mel frames/s",
+                     desc="base config, learned-alignment forward (aligner + MAS 8000x1000), one utterance of 1000 phonemes"),
     # configs[1] (N=1, fp32) / configs[2] (N>1): training step with learned alignment, batch 32 per GPU
     "train_c2": dict(kind="train", batch=32, src=(60, 80), metric="train_utts_per_sec", unit="utterances/s"),
     "mas_c2": dict(kind="mas", batch=32, F=500, T=80, metric="mas_ms_per_batch", unit="ms/batch"),
@@ -46,6 +55,16 @@ def flops_fwd(B, T, F, aligner=False):
     if aligner:
         f += T * 868_352 + F * 115_200 + F * T * 240
     return B * f
+
+
+def workload_string(wl_name, wl, B, T, F):
+    """One description per workload, shared by both arms (the driver compares the strings)."""
+    if wl["kind"] == "train":
+        return (f"{wl_name}: base config random init, training step with learned alignment (aligner+MAS, duration/pitch/energy/mel/"
+                f"postnet/CTC/bin losses, backward, clip 1.0, AdamW+Noam), B={B}/GPU, T<={T}, F<={F}")
+    if wl["kind"] == "synth":
+        return f"{wl_name}: {wl.get('desc', 'base config random init')}, teacher-forced synthesis forward, B={B}/GPU, T<={T}, F<={F}, 80-bin mel"
+    return wl_name
 
 
 def peaks():
@@ -122,9 +141,10 @@ def build_model(wl, device):
     from fastspeech2_lightning_b200.fs2.config import FastSpeech2Config
     from fastspeech2_lightning_b200.fs2.model import FastSpeech2
 
-    cfg = FastSpeech2Config(model=dict(learn_alignment=wl["learn_alignment"]))
+    cfg = FastSpeech2Config(model=dict(learn_alignment=wl["learn_alignment"], **wl.get("model_kw", {})))
     torch.manual_seed(1234)
-    model = FastSpeech2(cfg, stats=synthetic.DEFAULT_STATS)  # random init of the reference architecture
+    model = FastSpeech2(cfg, stats=synthetic.DEFAULT_STATS,  # random init of the reference architecture
+                        speaker2id={f"s{i}": i for i in range(wl.get("n_speakers", 0))})
     model.eval()
     if device is not None:
         model = model.to(device)
@@ -133,13 +153,24 @@ def build_model(wl, device):
     return cfg, model
 
 
-def make_batches(wl, n, rank):
+def make_batches(wl, n, rank, world=1):
     from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.parallel import shard_utterances
 
+    if wl.get("n_utts"):  # a corpus of n_utts utterances, length-sorted batches dealt round-robin to the ranks
+        g = torch.Generator().manual_seed(1234)
+        lengths = torch.randint(wl["src"][0], wl["src"][1] + 1, (wl["n_utts"],), generator=g).tolist()
+        mine = shard_utterances(lengths, rank, world, wl["batch"])
+        return [synthetic.make_batch(len(idx), wl["src"], seed=1234 + 17 * k + 1000 * rank, learn_alignment=False, inference=True,
+                                     teacher_forced=True, n_speakers=wl.get("n_speakers", 1), src_lens=[lengths[i] for i in idx],
+                                     style_frames=wl.get("style_frames", 0)) for k, idx in enumerate(mine)]
     out = []
     for i in range(n):
-        b = synthetic.make_batch(wl["batch"], wl["src"], seed=1234 + 1000 * rank + i, learn_alignment=wl["learn_alignment"],
-                                 inference=True, teacher_forced=True)
+        if wl.get("align_forward"):
+            b = synthetic.make_batch(wl["batch"], wl["src"], seed=1234 + 1000 * rank + i, learn_alignment=True, dur_range=wl.get("dur_range", (3, 9)))
+        else:
+            b = synthetic.make_batch(wl["batch"], wl["src"], seed=1234 + 1000 * rank + i, learn_alignment=wl["learn_alignment"],
+                                     inference=True, teacher_forced=True)
         out.append(b)
     return out
 
@@ -192,23 +223,27 @@ def run_ours(args, wl_name, wl, rank, world, device):
     if wl["kind"] == "train":
         return run_train(args, wl_name, wl, rank, world, device, pk)
     cfg, model = build_model(wl, device)
-    host_batches = [pin(b) for b in make_batches(wl, n_distinct, rank)]
+    host_batches = [pin(b) for b in make_batches(wl, n_distinct, rank, world)]
+    n_distinct = len(host_batches)
     dev_batches = [synthetic.batch_to(b, device) for b in host_batches]
     frames = [int(b["mel_lens"].sum()) for b in host_batches]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+    align_fwd = bool(wl.get("align_forward"))  # learned-alignment forward (mel given; aligner + MAS run), no gradient
 
     def step_eager(i):
         with torch.no_grad():
-            return model(dev_batches[i % n_distinct], inference=True)
+            return model(dev_batches[i % n_distinct]) if align_fwd else model(dev_batches[i % n_distinct], inference=True)
 
     l0 = ops.launch_count
     step_eager(0)
     launches_per_step = ops.launch_count - l0
-    if not args.eager:
+    if not args.eager and not align_fwd:
         model.enable_cuda_graphs()  # public switch: predict_step replays one CUDA graph per (B,T,F) shape
 
     def step(i):
         # inputs already resident in HBM; with graphs: device→device copy into the captured buffers + 1 graph launch
+        if align_fwd:
+            return step_eager(i)
         return model.predict_step(dev_batches[i % n_distinct], i)
 
     from fastspeech2_lightning_b200.fs2.batching import trim_predictions
@@ -216,6 +251,10 @@ def run_ours(args, wl_name, wl, rank, world, device):
     def step_e2e(i):
         # the calls a user makes: pinned-host batch in (predict_step), every utterance's valid frames back on the host as
         # [n_mels, T] (trim_predictions = the prediction-writing callback's per-item slicing, one launch + one D2H copy)
+        if align_fwd:
+            with torch.no_grad():
+                out = model(synthetic.batch_to(host_batches[i % n_distinct], device, non_blocking=True))
+            return trim_predictions(out, model.output_key, reuse_buffer=True)
         out = model.predict_step(host_batches[i % n_distinct] if not args.eager else
                                  synthetic.batch_to(host_batches[i % n_distinct], device, non_blocking=True), i)
         return trim_predictions(out, model.output_key, reuse_buffer=True)
@@ -285,7 +324,7 @@ def run_ours(args, wl_name, wl, rank, world, device):
         "metric": wl["metric"], "value": all_frames / (ms_dev * 1e-3), "unit": wl["unit"], "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[ops.PRECISION], "data": "synthetic",
-        "config": {"workload": f"{wl_name}: base config random init, teacher-forced synthesis forward, B={B}/GPU, T<={T}, F<={F}, 80-bin mel",
+        "config": {"workload": workload_string(wl_name, wl, B, T, F),
                    "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "parallelism": f"replicas x{world}, no collectives", "launch": "eager" if args.eager else "cuda graph replay"},
         "e2e": {"value": all_frames / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
                 "d2h_bytes_per_step": frames[0] * 80 * 4 + B * 8, "ms_per_step": ms_e2e / args.steps,
@@ -293,11 +332,11 @@ def run_ours(args, wl_name, wl, rank, world, device):
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": roof,
-        "step_flops": flops_fwd(B, T, F), "step_tflops": flops_fwd(B, T, F) / (ms_dev / args.steps * 1e-3) / 1e12,
+        "step_flops": flops_fwd(B, T, F, aligner=align_fwd), "step_tflops": flops_fwd(B, T, F, aligner=align_fwd) / (ms_dev / args.steps * 1e-3) / 1e12,
         "gpu_busy_ms_per_step": tot_ms / 2,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, cfg, host_batches[0])
+        line["cpu_baseline"] = reference_cpu_baseline(wl) or cpu_baseline(wl, cfg, host_batches[0])
     return line
 
 
@@ -417,8 +456,8 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPES[ops.PRECISION],
         "data": "synthetic",
-        "config": {"workload": f"{wl_name}: base config random init, training step with learned alignment (aligner+MAS, "
-                               f"duration/pitch/energy/mel/postnet/CTC/bin losses, backward, clip 1.0, AdamW+Noam), B={B}/GPU, T<={T}, F<={F}",
+        "config": {"workload": workload_string(wl_name, wl, B, T, F),
+                   "data_check": "BadDataError check (sum of MAS durations == mel_lens, a host sync per step in the reference) off in the timed steps; the first eager sight of every shape runs it",
                    "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}: per-rank replicas, one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "dp1",
                    "launch": ("cuda graph replay of the whole step (zero_grad, forward, losses, backward, clip, AdamW), one graph per batch shape"
@@ -432,9 +471,23 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         "gpu_busy_ms_per_step": tot_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs, cores = cpu_train_baseline(wl, steps=1)
-        line["cpu_baseline"] = {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
-                                "sample": f"oracle port (torch-CPU restatement, no dropout RNG) of one full training step on one batch of the workload: {secs:.1f} s"}
+        line["cpu_baseline"] = reference_cpu_baseline(wl)
+        if line["cpu_baseline"] is None:
+            v, secs, cores = cpu_train_baseline(wl, steps=1)
+            line["cpu_baseline"] = {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
+                                    "sample": f"oracle port (torch-CPU restatement, no dropout RNG) of one full training step on one batch of the workload: {secs:.1f} s"}
+        # context: the same unmodified reference modules as stock PyTorch eager on THIS GPU
+        try:
+            runner = reference_runner(wl, device=str(device))
+            if runner is not None:
+                v, secs, steps, _ = time_reference(runner, wl, 0, 6, 2, budget_s=30.0)
+                line.setdefault("also", {})["reference_torch_eager_on_this_gpu"] = {
+                    "metric": wl["metric"], "value": v, "unit": wl["unit"], "ms_per_step": secs * 1e3, "steps": steps,
+                    "note": "UNMODIFIED reference modules moved to the B200 (stock PyTorch eager: cuBLAS / cuDNN / ATen, MAS on the host via numba as the reference does); context, not an arm of this repo"}
+                del runner
+                torch.cuda.empty_cache()
+        except Exception as e:  # context only: never fail the bench for it
+            line.setdefault("also", {})["reference_torch_eager_on_this_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     return line
 
 
@@ -557,8 +610,64 @@ def cpu_baseline(wl, cfg, batch):
             "sample": f"oracle (torch-CPU restatement of the reference forward) on one batch of the workload ({frames} frames), best of 3, {best*1e3:.0f} ms"}
 
 
+def reference_runner(wl, device="cpu"):
+    """The UNMODIFIED reference model (oracle/ref_runner.py over /root/reference or its build-time copy oracle/_ref) with the
+    same random-init weights as our arm; None when the sources are not there (then the oracle port stands in)."""
+    from oracle import ref_runner
+
+    if not ref_runner.available():
+        return None
+    if wl["kind"] == "train":
+        cfg, model = build_train_model(None)
+    else:
+        cfg, model = build_model(wl, None)
+    extra = wl.get("model_kw", {})
+    return ref_runner.ReferenceRunner(cfg, model.state_dict(), device=device,
+                                      speaker2id={f"s{i}": i for i in range(extra.get("n_speakers", 0))},
+                                      lang2id={f"l{i}": i for i in range(extra.get("n_languages", 0))})
+
+
+def time_reference(runner, wl, rank, steps, warmup, budget_s=240.0):
+    """(value, seconds per step, steps actually timed, description).  Steps are cut (never below 2) only if the run would
+    not end within `budget_s`: a CPU training step of the real reference takes seconds."""
+    if wl["kind"] == "train":
+        batches = make_train_batches(wl, 2, rank)
+        fn, units = runner.train_step, [wl["batch"]] * 2
+    else:
+        batches = make_batches(wl, 2, rank)[:2]
+        if len(batches) == 1:
+            batches = batches * 2
+        fn = runner.align_forward if wl.get("align_forward") else runner.synthesize
+        units = [int(b["mel_lens"].sum()) for b in batches]
+    if runner.device.type != "cpu":
+        from fastspeech2_lightning_b200 import synthetic
+
+        batches = [synthetic.batch_to(b, runner.device) for b in batches]
+    sync = (lambda: torch.cuda.synchronize()) if runner.device.type != "cpu" else (lambda: None)
+    t0 = time.perf_counter()
+    fn(batches[0])  # first call: numba JIT of the MAS kernels, allocator warm-up
+    sync()
+    for i in range(max(warmup - 1, 0)):
+        fn(batches[(i + 1) % 2])
+    sync()
+    t = time.perf_counter()
+    fn(batches[0])
+    sync()
+    one = time.perf_counter() - t
+    steps = max(2, min(steps, int(budget_s / max(one, 1e-6))))
+    t = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        fn(batches[i % 2])
+        done += units[i % 2]
+    sync()
+    secs = time.perf_counter() - t
+    return done / secs, secs / steps, steps, time.perf_counter() - t0
+
+
 def run_reference(args, wl_name, wl, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    """--impl reference: the reference's own implementation of the path on the host cores (all threads): the UNMODIFIED
+    reference modules when their sources are available (kind "reference"), else the oracle port (kind "port")."""
     if rank != 0:
         return None
     cores = os.cpu_count() or 1
@@ -578,31 +687,45 @@ def run_reference(args, wl_name, wl, rank, world):
                 "ms_per_step": v, "higher_is_better": False, "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name},
                 "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port", "sample": "oracle b_mas (OpenMP over items)"},
                 "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if wl["kind"] == "train":
-        steps = min(args.steps, 2)  # a CPU training step takes several seconds
+    b0 = (make_train_batches if wl["kind"] == "train" else make_batches)(wl, 1, 0)[0]
+    B, T, F = wl["batch"], int(b0["max_src_len"]), int(b0["max_mel_len"])
+    runner = reference_runner(wl)
+    if runner is not None:
+        v, secs, steps, total = time_reference(runner, wl, 0, args.steps, args.warmup)
+        kind = "reference"
+        sample = (f"{steps} timed steps (of {args.steps} asked; {args.warmup} warm-up) of the same workload through the UNMODIFIED reference modules "
+                  f"(fs2.model.FastSpeech2 under oracle/ref_shim.py, torch CPU, numba MAS, dropout active in training), {secs:.2f} s/step, {total:.0f} s in all")
+    elif wl["kind"] == "train":
+        steps = min(args.steps, 2)
         v, secs, cores = cpu_train_baseline(wl, steps=steps)
-        return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": steps, "warmup": 1,
-                "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{wl_name}: base config random init, training step with learned alignment, B={wl['batch']}"},
-                "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
-                                 "sample": f"{steps} training steps of the same workload on the host CPU (oracle port; dropout RNG not included)"},
-                "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    cfg, _ = build_model(wl, None)
-    batches = make_batches(wl, 2, 0)
-    fns = [cpu_forward_fn(wl, cfg, b) for b in batches]
-    steps = min(args.steps, 8)  # bounded sample: a CPU step takes ~0.5-2 s
-    for i in range(min(args.warmup, 2)):
-        fns[i % 2]()
-    t = sum(_time(fns[i % 2]) for i in range(steps))
-    frames = sum(int(batches[i % 2]["mel_lens"].sum()) for i in range(steps))
-    v = frames / t
-    B, T, F = wl["batch"], int(batches[0]["max_src_len"]), int(batches[0]["max_mel_len"])
-    return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 2),
-            "ms_per_step": t / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl_name}: base config random init, teacher-forced synthesis forward, B={B}, T<={T}, F<={F}, 80-bin mel"},
-            "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
-                             "sample": f"{steps} steps of the same workload on the host CPU (oracle port: the reference is pure Python and /root/reference does not travel)"},
+        kind, sample = "port", f"{steps} training steps of the same workload on the host CPU (oracle port; dropout RNG not included; reference sources not found)"
+    else:
+        cfg, _ = build_model(wl, None)
+        batches = make_batches(wl, 2, 0)
+        fns = [cpu_forward_fn(wl, cfg, b) for b in batches]
+        steps = min(args.steps, 8)
+        for i in range(min(args.warmup, 2)):
+            fns[i % 2]()
+        t = sum(_time(fns[i % 2]) for i in range(steps))
+        v = sum(int(batches[i % 2]["mel_lens"].sum()) for i in range(steps)) / t
+        secs = t / steps
+        kind, sample = "port", f"{steps} steps of the same workload on the host CPU (oracle port; reference sources not found)"
+    return {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(wl_name, wl, B, T, F)},
+            "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def reference_cpu_baseline(wl, budget_s=25.0):
+    """cpu_baseline of the main arm: a bounded sample (≈ 10–30 s of CPU work) of the same workload through the real reference."""
+    runner = reference_runner(wl)
+    if runner is None:
+        return None
+    v, secs, steps, total = time_reference(runner, wl, 0, 4, 1, budget_s=budget_s)
+    return {"value": v, "unit": wl["unit"], "cores": os.cpu_count() or 1, "kind": "reference",
+            "sample": f"{steps} steps of the same workload through the UNMODIFIED reference modules on the host CPU (dropout active in training), "
+                      f"{secs:.2f} s/step after a JIT / warm-up step"}
 
 
 def main():
@@ -641,7 +764,7 @@ def main():
         # the other two headline numbers of BASELINE.json's metric (mel frames/s synthesized, MAS ms/batch)
         import copy
 
-        line["also"] = {}
+        line.setdefault("also", {})
         for entry in [n for n in args.also.split(",") if n and n != args.workload]:
             # "synth_c1@tf32": the same workload in single-pass TF32; "synth_c1@dec-tf32": only the decoder / PostNet
             # (everything after the last discrete decision) in single-pass TF32 — the reduced-precision configuration

@@ -281,6 +281,11 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 
 using namespace fs2k;
 
+bool fs2k_gemm_bf16_panel_ok(int K, int N, int taps, int a_is_bf16, bool has_lo, bool has_scale);
+int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const void* W, int w_mn, int N, const float* bias, int act,
+                                float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, void* C16,
+                                int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, cudaStream_t s);
+
 extern "C" int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream) {
     FS2K_REQUIRE(n >= 0, FS2K_ERR_BAD_SHAPE);
     if (n == 0) return FS2K_OK;
@@ -323,6 +328,11 @@ extern "C" int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int 
                      (!(P32 || P16) || (ldp & 3) == 0), FS2K_ERR_UNSUPPORTED);
     const int nsplit = W_lo ? 3 : 1;
     FS2K_REQUIRE(nsplit == 1 || !a_is_bf16, FS2K_ERR_UNSUPPORTED);  // the lo part of A comes from its fp32 source
+    // the model's dominant class (fp32 activations, K <= 256, one tap): row-panel kernel, gemm_bf16_panel.cu
+    // (block_n_hint < 0 forces the tile-per-CTA kernel below — A/B measurements)
+    if (block_n_hint >= 0 && fs2k_gemm_bf16_panel_ok(K, N, taps, a_is_bf16, W_lo != nullptr, scale != nullptr))
+        return fs2k_gemm_bf16_panel_launch((const float*)A, lda, M, K, W_hi, w_mn, N, bias, act, alpha, residual, ldr, row_mask, C, ldc,
+                                           C16, ldc16, P32, P16, ldp, dropout_p, seed, (cudaStream_t)stream);
     int block_n = N <= 256 ? N : 128;
     if (N > 128 && N % 128 == 0) block_n = 128;            // two CTAs per SM: epilogue of one overlaps the other's main loop
     if (block_n_hint == 256 && N % 256 == 0) block_n = 256;

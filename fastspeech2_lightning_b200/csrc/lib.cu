@@ -67,12 +67,13 @@ extern "C" int fs2k_seed_base_set_norms_bwd(const void*);
 extern "C" int fs2k_seed_base_set_gemm_tc(const void*);
 extern "C" int fs2k_seed_base_set_gemm_bf16(const void*);
 extern "C" int fs2k_seed_base_set_attention_tc(const void*);
+extern "C" int fs2k_seed_base_set_gemm_bf16_panel(const void*);
 
 extern "C" int fs2k_set_dropout_seed_base(const unsigned long long* device_counter) {
     int (*setters[])(const void*) = {fs2k_seed_base_set_attention_bwd, fs2k_seed_base_set_attention, fs2k_seed_base_set_dropout,
                                      fs2k_seed_base_set_gemm_bwd,      fs2k_seed_base_set_norms,     fs2k_seed_base_set_norms_bwd,
                                      fs2k_seed_base_set_gemm_tc,       fs2k_seed_base_set_gemm_bf16,
-                                     fs2k_seed_base_set_attention_tc};
+                                     fs2k_seed_base_set_attention_tc,  fs2k_seed_base_set_gemm_bf16_panel};
     for (auto f : setters) {
         const int r = f(device_counter);
         if (r != FS2K_OK) return r;

@@ -91,6 +91,8 @@ def make_batch(
     n_speakers: int = 1,
     n_languages: int = 1,
     first_is_longest: bool = True,
+    src_lens=None,
+    style_frames: int = 0,
     device: str | torch.device = "cpu",
 ) -> dict:
     """A batch dict as `FastSpeech2DataModule.collate_method` would build it.
@@ -101,12 +103,17 @@ def make_batch(
     * `inference=True`: `mel=None`, pitch=energy=None; with `teacher_forced` the integer
       durations and `mel_lens` are supplied (model.py:162-165), otherwise `mel_lens=None`,
       `max_mel_len=1_000_000` (dataset.py:263-268).
+    * `src_lens=[...]` fixes the phone count of every utterance; `style_frames > 0` adds a GST style reference mel.
     """
     g = _rng(seed, "batch")
     lo, hi = src_len_range
-    src_lens = g.integers(lo, hi + 1, size=batch_size)
-    if first_is_longest:
-        src_lens[0] = hi
+    if src_lens is not None:  # explicit phone counts (length-sorted batches of a corpus: bench synth_c4)
+        src_lens = np.asarray(src_lens, dtype=np.int64)
+        batch_size = len(src_lens)
+    else:
+        src_lens = g.integers(lo, hi + 1, size=batch_size)
+        if first_is_longest:
+            src_lens[0] = hi
     T = int(src_lens.max())
     text = np.zeros((batch_size, T), dtype=np.int32)
     dur = np.zeros((batch_size, T), dtype=np.int32)
@@ -129,6 +136,8 @@ def make_batch(
         "language": ["default"] * batch_size,
         "raw_text": [""] * batch_size,
     }
+    if style_frames:  # GST style reference mel [B, style_frames, n_mels] (fs2/model.py:196-199)
+        batch["mel_style_reference"] = torch.from_numpy(g.standard_normal((batch_size, style_frames, n_mels)).astype(np.float32))
     frame_valid = np.arange(F)[None, :] < mel_lens[:, None]
     if inference:
         batch["mel"] = None

@@ -151,7 +151,9 @@ int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, i
  *         data-gradient GEMM dX = G * W of a layer whose forward weights are that same array (no transposed copy)
  *   outputs (each optional, at least one): C fp32 / C16 bf16 = the final value; P32 / P16 (stride ldp) = acc + bias,
  *         the pre-activation saved for the backward.
- * block_n_hint: 0 = automatic column tile; 256 = wide tile for compute-bound shapes.
+ * block_n_hint: 0 = automatic; 256 = wide tile for compute-bound shapes; < 0 = never the row-panel kernel.
+ * fp32 A with K <= 256 (K % 64 == 0), one tap, N % 128 == 0 runs the row-panel kernel (gemm_bf16_panel.cu): A panel
+ * read once and resident in shared memory, two TMEM accumulators, epilogue overlapped with the next tile's MMAs.
  * fs2k_gemm_bf16_supported: K % 8 == 0 (w_mn = 0) / N % 8 == 0 (w_mn = 1), lda % 4 == 0 (fp32 A) or % 8 (bf16 A),
  * N % 16 == 0 (N <= 256) or N % 128 == 0. */
 int fs2k_gemm_bf16_supported(int K, int N, int lda, int taps, int a_is_bf16, int w_mn);

@@ -40,29 +40,33 @@ def rand(*shape, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(dev())
 
 
-@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 256, 256), (1000, 256, 1024), (777, 1024, 256), (513, 256, 768), (200, 80, 512), (260, 512, 80), (96, 256, 32)])
-def test_gemm_bf16_linear(M, K, N):
+@pytest.mark.parametrize("hint", [0, -1])  # 0: row-panel kernel where the shape allows; -1: always the tile-per-CTA kernel
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 256, 256), (1000, 256, 1024), (777, 1024, 256), (513, 256, 768), (200, 80, 512),
+                                   (260, 512, 80), (96, 256, 32), (16000, 256, 1024), (2560, 256, 1024), (129, 128, 384)])
+def test_gemm_bf16_linear(M, K, N, hint):
     a, w = rand(M, K, seed=1), rand(N, K, seed=2, scale=K ** -0.5)
     bias = rand(N, seed=3, scale=0.1)
     w16, _ = ops().cast_bf16(w)
-    c, _, _ = ops().gemm_bf16(a, w16, bias)
+    c, _, _ = ops().gemm_bf16(a, w16, bias, block_n_hint=hint)
     want = (r16(a).double() @ r16(w).double().T + bias.double()).float()
     assert rel(c, want) <= ACC_TOL, rel(c, want)
     assert rel(c, (a.double() @ w.double().T + bias.double()).float()) <= BF16_TOL
 
 
-def test_gemm_bf16_epilogue_outputs():
+@pytest.mark.parametrize("hint", [0, -1])
+def test_gemm_bf16_epilogue_outputs(hint):
     M, K, N = 500, 256, 1024
     a, w, bias, res = rand(M, K, seed=1), rand(N, K, seed=2, scale=K ** -0.5), rand(N, seed=3, scale=0.1), rand(M, N, seed=4)
     mask = (torch.arange(M, device=dev()) % 7 != 0)
     w16, _ = ops().cast_bf16(w)
-    c, c16, pre = ops().gemm_bf16(a, w16, bias, act="silu", alpha=0.5, residual=res, row_mask=mask, want_c16=True, want_pre="fp32")
+    c, c16, pre = ops().gemm_bf16(a, w16, bias, act="silu", alpha=0.5, residual=res, row_mask=mask, want_c16=True, want_pre="fp32",
+                                  block_n_hint=hint)
     z = (r16(a).double() @ r16(w).double().T + bias.double())
     want = ((F.silu(z) * 0.5 + res.double()) * mask[:, None]).float()
     assert rel(pre, z.float()) <= ACC_TOL
     assert rel(c, want) <= ACC_TOL
     assert torch.equal(c16, c.to(torch.bfloat16))
-    _, _, pre16 = ops().gemm_bf16(a, w16, bias, act="relu", want_c=False, want_c16=True, want_pre="bf16")
+    _, _, pre16 = ops().gemm_bf16(a, w16, bias, act="relu", want_c=False, want_c16=True, want_pre="bf16", block_n_hint=hint)
     assert torch.equal(pre16, pre.to(torch.bfloat16))
 
 
@@ -97,12 +101,13 @@ def test_gemm_bf16_split3_is_fp32_accurate(M, K, N):
     assert rel(c, want) <= 5e-5, rel(c, want)   # hi·hi + hi·lo + lo·hi: the dropped lo·lo term is 2^-16 relative per product
 
 
-@pytest.mark.parametrize("M,Nf,Kf", [(300, 256, 256), (500, 1024, 256), (400, 256, 1024), (260, 80, 512), (200, 512, 80)])
-def test_gemm_bf16_dgrad_reads_weights_mn_major(M, Nf, Kf):
+@pytest.mark.parametrize("hint", [0, -1])
+@pytest.mark.parametrize("M,Nf,Kf", [(300, 256, 256), (500, 1024, 256), (400, 256, 1024), (260, 80, 512), (200, 512, 80), (16000, 256, 1024)])
+def test_gemm_bf16_dgrad_reads_weights_mn_major(M, Nf, Kf, hint):
     """dX[m,k] = Σ_n G[m,n]·W[n,k] with the forward weight array W [Nf,Kf] itself as the (MN-major) operand."""
     g, w = rand(M, Nf, seed=11), rand(Nf, Kf, seed=12, scale=Nf ** -0.5)
     w16, _ = ops().cast_bf16(w)
-    dx, _, _ = ops().gemm_bf16(g, w16.reshape(1, Nf, Kf), None, w_mn=True)
+    dx, _, _ = ops().gemm_bf16(g, w16.reshape(1, Nf, Kf), None, w_mn=True, block_n_hint=hint)
     want = (r16(g).double() @ r16(w).double()).float()
     assert rel(dx, want) <= ACC_TOL, rel(dx, want)
 
@@ -204,3 +209,18 @@ def test_attention_tc_dropout_is_consistent_between_forward_dq_and_dkv():
     ones[..., 2 * D:] = 1.0
     o1 = ops().attention_bf16(ops().cast_bf16(ones)[0], torch.tensor([256], dtype=torch.int32, device=dev()), H, dropout_p=p, seed=7)
     assert abs(float(o1.mean()) - 1.0) < 2e-2   # E[dropout(P)·1] = 1
+
+
+def test_gemm_bf16_dropout_mask_matches_the_backward_kernel():
+    """The GEMM epilogue's dropout (both kernels) and act_bwd regenerate the same counter-hash mask."""
+    M, K, N, p, seed = 700, 256, 512, 0.3, 99
+    a, w = rand(M, K, seed=31), rand(N, K, seed=32, scale=K ** -0.5)
+    w16, _ = ops().cast_bf16(w)
+    base, _, _ = ops().gemm_bf16(a, w16, None)
+    for hint in (0, -1):
+        y, _, _ = ops().gemm_bf16(a, w16, None, dropout_p=p, seed=seed, block_n_hint=hint)
+        keep = y != 0
+        assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
+        assert torch.allclose(y[keep], base[keep] / (1 - p), rtol=1e-5, atol=1e-6)
+        gz = ops().act_bwd(torch.ones_like(y), None, None, 1.0, None, p, seed)
+        assert torch.equal(gz != 0, keep | (base == 0))
