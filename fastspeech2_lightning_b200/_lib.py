@@ -70,7 +70,7 @@ class _ProfilingProxy:
 
     def __getattr__(self, name):
         fn = getattr(self._cdll, name)
-        if (not name.startswith("fs2k_") or name in ("fs2k_strerror", "fs2k_version", "fs2k_check_device", "fs2k_spin_ns")
+        if (not name.startswith("fs2k_") or name in ("fs2k_strerror", "fs2k_version", "fs2k_check_device")
                 or name.endswith(("_bytes", "_supported"))):
             return fn
 

@@ -42,15 +42,7 @@ struct TcEpilogue {
     const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_out; int ld_ln;
     const float* ln2_gamma; const float* ln2_beta; float* ln2_out;  // second LN chained on ln_out
     float drop_p; unsigned long long seed;  // dropout of the value before the residual add (mask = hash(seed, m·N + n))
-    unsigned long long* dbg;  // optional: 8 globaltimer stamps of CTA (0,0) (profiling aid, normally null)
 };
-__device__ __forceinline__ void tc_stamp(const TcEpilogue& ep, int slot) {
-    if (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        ep.dbg[slot] = t;
-    }
-}
 
 // K-major operand whose rows are one swizzle atom wide (BK·4 = 128 or 64 bytes): 8-row groups are 8·row bytes apart
 // (SBO), descriptor version 1, layout type SWIZZLE_128B (2) or SWIZZLE_64B (4)
@@ -125,7 +117,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nk = (K + TC_BK - 1) / TC_BK;
     const int iters = taps * nk;
 
-    if (threadIdx.x == 0) tc_stamp(ep, 0);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
@@ -145,7 +136,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
     pdl_wait();  // barrier init + TMEM allocation above overlapped the previous kernel's tail; memory is touched below
-    if (threadIdx.x == 0) tc_stamp(ep, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -172,7 +162,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int it = 0; it < iters; ++it) {
                 const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 mbar_wait(smem_u32(PASSES == 3 ? &s_split[s] : &s_full[s]), ph);
-                if (it == 0) tc_stamp(ep, 2);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
 #pragma unroll
@@ -189,7 +178,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs have read it
             }
             tc_commit(smem_u32(&s_tmem_full));
-            tc_stamp(ep, 3);
         }
     } else if (warp >= 4) {
         const int et = threadIdx.x - 128;  // 0..255 among the epilogue warps
@@ -207,7 +195,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // ===== epilogue stage 1: raw accumulators TMEM → registers → staging tile (row = TMEM lane) =====
         mbar_wait(smem_u32(&s_tmem_full), 0);
-        if (et == 0) tc_stamp(ep, 4);
         tc_fence_after();
         const int q = warp & 3;              // TMEM lane quadrant this warp may read
         const int half = (warp - 4) >> 2;    // two warps share a quadrant and alternate 16-column chunks
@@ -224,7 +211,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
     }
     __syncthreads();
-    if (threadIdx.x == 0) tc_stamp(ep, 5);
 
     // ===== epilogue stage 2 (all warps): column math, residual, row mask, LayerNorm, coalesced 16-byte stores =====
     {
@@ -330,7 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) tc_stamp(ep, 6);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
@@ -341,13 +326,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }  // namespace fs2k
 
 using namespace fs2k;
-
-static unsigned long long* g_tc_debug_stamps = nullptr;
-// profiling aid: device buffer of 8 uint64 receiving globaltimer stamps of CTA (0,0) of later fs2k_gemm_tc launches
-extern "C" int fs2k_gemm_tc_set_debug_stamps(void* device_buffer) {
-    g_tc_debug_stamps = (unsigned long long*)device_buffer;
-    return FS2K_OK;
-}
 
 extern "C" int fs2k_gemm_tc_supported(int K, int N, int lda, int taps) {
     if (K <= 0 || N <= 0 || taps < 1) return 0;
@@ -421,8 +399,7 @@ extern "C" int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const 
         if (r != CUDA_SUCCESS) return fs2k_set_cuda_error(cudaErrorInvalidValue);
     }
     TcEpilogue ep{bias, scale, shift, act, alpha, residual, ldr, row_mask, C, ldc,
-                  ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out, dropout_p, (unsigned long long)seed,
-                  g_tc_debug_stamps};
+                  ln_gamma, ln_beta, ln_eps, ln_out, N, ln2_gamma, ln2_beta, ln2_out, dropout_p, (unsigned long long)seed};
     const size_t stage = (size_t)(TC_BM + block_n) * bk * 4 * (passes == 3 ? 2 : 1);
     int n_stages = (int)((226 * 1024) / stage);
     const int max_stages = passes == 3 ? TC_MAX_STAGES : 4;

@@ -39,24 +39,6 @@ extern "C" int fs2k_check_device(void) {
     return major == 10 ? FS2K_OK : FS2K_ERR_ARCH;
 }
 
-// Occupies the stream for `ns` nanoseconds (bench.py's roofline pass queues work behind it so that the
-// per-kernel CUDA-event timings that follow are not stretched by host launch gaps).
-__global__ void spin_kernel(unsigned long long ns) {
-    pdl_wait();
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    } while (t - t0 < ns);
-}
-
-extern "C" int fs2k_spin_ns(long ns, fs2k_stream_t stream) {
-    FS2K_REQUIRE(ns >= 0 && ns <= 2000000000L, FS2K_ERR_BAD_SHAPE);
-    fs2k_launch(spin_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long)ns);
-    FS2K_CHECK_LAUNCH();
-    return FS2K_OK;
-}
-
 // every translation unit with dropout kernels keeps its own copy of the seed-base pointer (common.cuh)
 extern "C" int fs2k_seed_base_set_attention_bwd(const void*);
 extern "C" int fs2k_seed_base_set_attention(const void*);

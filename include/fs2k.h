@@ -43,8 +43,6 @@ int fs2k_check_device(void); /* FS2K_OK iff the current device is compute capabi
 /* Programmatic dependent launch for every kernel of the library (default on): the next kernel of a stream / graph is
  * scheduled while the previous one drains and waits in griddepcontrol.wait before touching memory.  0 = plain launches. */
 int fs2k_set_pdl(int enabled);
-/* keeps `stream` busy for ns nanoseconds (measurement aid: lets the host queue work ahead of the GPU) */
-int fs2k_spin_ns(long ns, fs2k_stream_t stream);
 
 /* ---- monotonic alignment search -------------------------------------------------------------
  * replaces VarianceAdaptor.binarize_attention (fs2/variance_adaptor.py:160-181) and
@@ -135,8 +133,6 @@ int fs2k_gemm_f32(const float* A, int lda, int B, int L, int K, const float* W, 
  * fs2k_gemm_tc_supported: K % 4 == 0, lda % 4 == 0, N % 16 == 0 (N <= 256)
  * or N % 128 == 0. */
 int fs2k_gemm_tc_supported(int K, int N, int lda, int taps);
-/* profiling aid: 8 uint64 globaltimer stamps of CTA (0,0) of subsequent fs2k_gemm_tc launches (NULL switches it off) */
-int fs2k_gemm_tc_set_debug_stamps(void* device_buffer);
 int fs2k_gemm_tc(const float* A, int lda, int B, int L, int K, const float* W, int N, int taps, int pad,
                  const float* bias, const float* scale, const float* shift, int act, float alpha,
                  const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, const float* ln_gamma,

@@ -245,11 +245,13 @@ def test_training_step_gradients_match_reference(name, bwd, request):
         rel = abs(float(gr.norm()) - norm) / max(norm, 1e-6)
         worst = max(worst, rel)
         print(f"  {rel:.2e} {n}") if rel > 1e-3 else None
-        assert rel <= (2e-3 if bwd is None else 1e-2), f"{n}: |grad| {float(gr.norm()):.6e} vs reference {norm:.6e}"
+        # 3×TF32 forward and backward: measured worst case 2.7e-5; 2e-4 leaves headroom for a different
+        # summation order, not for a wrong term.  Single-pass TF32 gradients (the `bwd` variants) carry ≈ 1e-3 rounding.
+        assert rel <= (2e-4 if bwd is None else 1e-2), f"{n}: |grad| {float(gr.norm()):.6e} vs reference {norm:.6e}"
         h = torch.zeros(16, dtype=torch.float64)
         h[: min(16, gr.numel())] = gr[:16]
         scale = max(float(np.abs(head).max()), norm / max(gr.numel(), 1) ** 0.5, 1e-9)
-        assert float((h - torch.from_numpy(head).double()).abs().max()) <= (5e-3 if bwd is None else 3e-2) * scale + 1e-7, n
+        assert float((h - torch.from_numpy(head).double()).abs().max()) <= (5e-4 if bwd is None else 3e-2) * scale + 1e-7, n
     for k, want in gold.items():
         if k.startswith("bn."):
             close(model.state_dict()[k[3:]], want, 1e-4, k)
