@@ -46,7 +46,8 @@ WORKLOADS = {
 
 
 DTYPES = {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor cores)",
-          "bf16": "bf16 (tcgen05 kind::f16 operands; fp32 accumulate, residual stream, norms, softmax, master weights)"}
+          "bf16": "bf16 (tcgen05 kind::f16 operands; fp32 accumulate, residual stream, norms, softmax, master weights)",
+          "bf16x3": "f32 (3xBF16 split accumulation on kind::f16 tensor cores)"}
 
 
 def flops_fwd(B, T, F, aligner=False):
@@ -738,8 +739,8 @@ def main():
     ap.add_argument("--also", default="synth_c1,synth_c1@dec-tf32,mas_c2", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3", "bf16"])
-    ap.add_argument("--backward-precision", default=None, choices=["fp32", "tf32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3"])
+    ap.add_argument("--backward-precision", default=None, choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

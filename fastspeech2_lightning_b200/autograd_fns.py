@@ -126,7 +126,7 @@ def _prefetch_wt(w_taps, needs_dx):
     the bf16 mode, whose dgrad reads the forward weights as an MN-major operand."""
     if _SINK is None or not needs_dx:
         return None
-    if ops.PRECISION == "bf16" and ops.bf16_dgrad_ok(w_taps):
+    if ops.PRECISION in ("bf16", "bf16x3") and ops.bf16_dgrad_ok(w_taps):
         return None
     return _SINK.prefetch_transposed(w_taps)
 

@@ -289,6 +289,9 @@ def conv_weight_taps(weight: torch.Tensor) -> torch.Tensor:
 #            softmax / master weights (BASELINE configs[2]).  Applies to the Conformer stacks, mel_linear and PostNet;
 #            what feeds a discrete decision (aligner → MAS, variance predictors → bucketize / durations) runs under
 #            `full_precision()` and stays 3×TF32, so alignments, durations and teacher-forced bucket ids do not move.
+#   "bf16x3" fp32-level accuracy on the bf16 tensor-core path: activations and weights split as hi + lo (two bf16 each),
+#            hi·hi + hi·lo + lo·hi accumulated in fp32 (dropped term 2^-16 per product) — 3 kind::f16 MMAs cost half of
+#            3 kind::tf32 ones and the operand tiles are half the size.  Weight gradients and attention as in "tf32x3".
 PRECISION = "tf32x3"
 
 
@@ -306,7 +309,7 @@ DECODER_PRECISION = None
 def set_precision(mode: str, backward: str | None = None, decoder: str | None = None) -> None:
     global PRECISION, BACKWARD_PRECISION, DECODER_PRECISION
     for m in (mode, backward, decoder):
-        if m not in (None, "fp32", "tf32", "tf32x3", "bf16"):
+        if m not in (None, "fp32", "tf32", "tf32x3", "bf16", "bf16x3"):
             raise ValueError(m)
     PRECISION = mode
     BACKWARD_PRECISION = backward
@@ -377,7 +380,7 @@ def gemm(a, w, bias=None, *, taps_pad: int = 0, scale=None, shift=None, act=None
     ln = (gamma, beta, eps): also return LayerNorm(result) — fused into the tensor-core epilogue when one
     tile spans the row, otherwise a separate fs2k_layernorm_fwd launch; ln2 = (gamma, beta) chains a second
     LayerNorm on the first one's output.  Returns C, or (C, ln_out[, ln2_out]) when ln is given."""
-    if PRECISION == "bf16" and ln is None:
+    if PRECISION in ("bf16", "bf16x3") and ln is None:
         r = _gemm_bf16_auto(a, w, bias, taps_pad, scale, shift, act, alpha, residual, row_mask, out, dropout_p, seed)
         if r is not None:
             return r
@@ -416,11 +419,11 @@ def _gemm_bf16_auto(a, w, bias, taps_pad, scale, shift, act, alpha, residual, ro
     """The bf16-mode path of gemm(): fp32 weights `w` → their bf16 shadow / cached cast; None when the shape is not taken."""
     if not _bf16_shape_ok(a, w, False):
         return None
-    w16, _ = bf16_weight(w)
+    w16, wlo = bf16_weight(w, want_lo=PRECISION == "bf16x3")
     K = a.shape[-1]
     taps = 1 if w.dim() == 2 else w.shape[0]
     hint = 256 if taps * K >= 1024 and w16.shape[-2] % 256 == 0 else 0  # compute-bound shapes (PostNet): wide tiles
-    c, _, _ = gemm_bf16(a, w16, bias, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha, residual=residual,
+    c, _, _ = gemm_bf16(a, w16, bias, w_lo=wlo, taps_pad=taps_pad, scale=scale, shift=shift, act=act, alpha=alpha, residual=residual,
                         row_mask=row_mask, dropout_p=dropout_p, seed=seed, block_n_hint=hint, out=out)
     return c
 
@@ -429,19 +432,19 @@ def gemm_dgrad(g, w_taps, pad: int, wt=None):
     """dX of y = conv(x, W): g [B,L,N] · W [taps,N,K] → [B,L,K].  bf16 mode: the forward weights themselves are the
     (MN-major) operand; otherwise `wt` / a transposed re-pack feeds the forward kernel."""
     taps = w_taps.shape[0]
-    if PRECISION == "bf16" and bf16_dgrad_ok(w_taps) and not (g.data_ptr() & 15):
-        w16, _ = bf16_weight(w_taps)
+    if PRECISION in ("bf16", "bf16x3") and bf16_dgrad_ok(w_taps) and not (g.data_ptr() & 15):
+        w16, wlo = bf16_weight(w_taps, want_lo=PRECISION == "bf16x3")
         hint = 256 if taps * w_taps.shape[1] >= 1024 and w_taps.shape[2] % 256 == 0 else 0
-        return gemm_bf16(g, w16, None, w_mn=True, taps_pad=taps - 1 - pad, block_n_hint=hint)[0]
+        return gemm_bf16(g, w16, None, w_lo=wlo, w_mn=True, taps_pad=taps - 1 - pad, block_n_hint=hint)[0]
     return gemm(g, wt if wt is not None else weight_taps_transposed(w_taps), None, taps_pad=taps - 1 - pad)
 
 
 def gemm_silu_pair(a, w, bias, taps_pad: int = 0, residual=None, dropout_p: float = 0.0, seed: int = 0):
     """(pre, y): pre = conv(a, W) + b, y = dropout(silu(pre)) + residual — one launch in the bf16 mode (the epilogue
     writes both), else the GEMM followed by the fused SiLU + dropout elementwise kernel."""
-    if PRECISION == "bf16" and _bf16_shape_ok(a, w, False):
-        w16, _ = bf16_weight(w)
-        y, _, pre = gemm_bf16(a, w16, bias, taps_pad=taps_pad, act="silu", residual=residual, want_pre="fp32",
+    if PRECISION in ("bf16", "bf16x3") and _bf16_shape_ok(a, w, False):
+        w16, wlo = bf16_weight(w, want_lo=PRECISION == "bf16x3")
+        y, _, pre = gemm_bf16(a, w16, bias, w_lo=wlo, taps_pad=taps_pad, act="silu", residual=residual, want_pre="fp32",
                               dropout_p=dropout_p, seed=seed)
         return pre, y
     pre = gemm(a, w, bias, taps_pad=taps_pad)

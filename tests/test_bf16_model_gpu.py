@@ -151,3 +151,45 @@ def test_bf16_graph_replayed_training_step_matches_eager_steps():
         for k in a:
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
     assert runs["graph"][0][-1]["total"] < runs["graph"][0][0]["total"]
+
+
+@pytest.mark.parametrize("name", ["train_eval", "train_bn", "infer_tf", "train_frame_level"])
+def test_bf16x3_split_mode_is_fp32_accurate(name):
+    """`ops.set_precision("bf16x3")`: hi/lo bf16 split of both operands, three kind::f16 MMAs per k-step.  The forward
+    outputs must meet the fp32 bar (max err ≤ 1e-4 of max|ref|) on the goldens; gradient-norm errors are reported."""
+    from fastspeech2_lightning_b200 import ops
+    from test_ops_gpu import close
+
+    meta, gold = load_case(name)
+    model = build_model(meta)
+    batch = case_batch(meta, DEV)
+    ops.set_precision("bf16x3")
+    out = model(batch, inference=meta["inference"]) if not meta["inference"] else None
+    if out is None:
+        with torch.no_grad():
+            out = model(batch, inference=True)
+    worst = 0.0
+    for k, want in gold.items():
+        if not k.startswith("out.") or out.get(k[4:]) is None:
+            continue
+        got = out[k[4:]].detach().cpu()
+        if want.dtype.kind in "biu" or k == "out.attn_hard":
+            assert np.array_equal(got.numpy().astype(want.dtype), want), k
+            continue
+        w = torch.from_numpy(want)
+        fin = torch.isfinite(w)
+        err = float((got[fin] - w[fin]).abs().max() / w[fin].abs().max().clamp_min(1e-6))
+        worst = max(worst, err)
+        assert err <= 1e-4, (k, err)
+    print(f"{name}: bf16x3 worst forward error {worst:.2e} of max|ref|")
+    if "grad.norms" in gold:
+        losses = model.loss(out, batch, model.current_epoch)
+        losses["total"].backward()
+        params = dict(model.named_parameters())
+        gworst = 0.0
+        for n, norm in zip([str(x) for x in gold["grad.names"]], gold["grad.norms"]):
+            if norm < 1e-6:
+                continue
+            gworst = max(gworst, abs(float(params[n].grad.double().norm()) - norm) / norm)
+        print(f"{name}: bf16x3 worst relative gradient-norm error {gworst:.2e}")
+        assert gworst <= 2e-4, gworst
