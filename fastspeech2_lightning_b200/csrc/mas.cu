@@ -162,6 +162,116 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
     for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
 }
 
+// T ≤ 1024 (one column per thread): the same recurrence WITHOUT a block barrier per frame.  Row i of warp w needs only the
+// last column of warp w−1 from row i−1, so the warps run as a skewed wavefront: every warp publishes its boundary value
+// into a ring of MAS_RING rows and then its row counter; its right neighbour spins on that counter (shared memory,
+// ≈ 30-cycle polls) instead of the whole CTA meeting at __syncthreads (≈ 370 ns per frame with 32 warps).  A warp may
+// run at most MAS_RING − 1 rows ahead of its right neighbour (ring-slot reuse guard).  Direction words go straight to
+// global memory (one 4-byte store per warp and frame, nothing waits for it).  Arithmetic, tie rule and outputs are
+// those of mas_dp_kernel — bit-exact against the reference.
+constexpr int MAS_RING = 64;
+
+template <int PF>
+__global__ void __launch_bounds__(1024, 1)
+mas_dp_wave_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
+                   int W, uint32_t* __restrict__ dirs, int* __restrict__ path, int* __restrict__ durations) {
+    pdl_wait();
+    extern __shared__ float ring[];  // [PF][blockDim]
+    __shared__ float bnd[MAS_RING][32];
+    __shared__ int progress[32];     // last row whose boundary value warp w has published
+    const int b = blockIdx.x;
+    const int n_text = min(in_lens[b], T);
+    const int n_mel = min(out_lens[b], F);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float NEG_INF = -INFINITY;
+    const float* x = attn + (size_t)b * F * T;
+    uint32_t* d = dirs + (size_t)b * F * W;
+    int* p = path + (size_t)b * F;
+    int* dur = durations + (size_t)b * T;
+
+    for (int t = tid; t < T; t += blockDim.x) dur[t] = 0;
+    for (int f = max(n_mel, 0) + tid; f < F; f += blockDim.x) p[f] = -1;
+    if (n_mel <= 0 || n_text <= 0) {
+        for (int f = tid; f < F; f += blockDim.x) p[f] = -1;
+        return;
+    }
+    const int col = tid;
+    const bool live = col < n_text;
+    float prev = NEG_INF;
+    if (col == 0) prev = x[0];  // row 0: log_p[0,0] = x[0,0]; log_p[0,1:] = -inf (alignment.py:53-54)
+    if (lane == 31) bnd[0][warp] = prev;
+    if (lane == 0) progress[warp] = 0;
+    auto issue = [&](int r) {
+        if (r < n_mel && live) cp_async4(ring + (size_t)(r % PF) * blockDim.x + tid, x + (size_t)r * T + col);
+        cp_async_commit();
+    };
+    for (int r = 1; r <= PF; ++r) issue(r);
+    __syncthreads();
+    volatile int* vprog = progress;
+    volatile float* vbnd = &bnd[0][0];
+
+    for (int i = 1; i < n_mel; ++i) {
+        cp_async_wait<PF - 1>();
+        const float xv = live ? ring[(size_t)(i % PF) * blockDim.x + tid] : 0.f;
+        float left = __shfl_up_sync(0xffffffffu, prev, 1);
+        if (lane == 0) {
+            if (warp == 0) {
+                left = NEG_INF;
+            } else {
+                while (vprog[warp - 1] < i - 1) {}
+                __threadfence_block();
+                left = vbnd[((i - 1) % MAS_RING) * 32 + warp - 1];
+            }
+        }
+        const float up = prev;
+        const bool diag = (left >= up) && (col >= 1);  // backtrack predicate of alignment.py:68; column 0 never moves
+        const uint32_t word = __ballot_sync(0xffffffffu, diag && live);
+        if (lane == 0 && warp < W) d[(size_t)i * W + warp] = word;
+        const float m = up > left ? up : left;
+        const float cur = live ? __fadd_rn(xv, m) : NEG_INF;
+        prev = cur;
+        if (lane == 31) {
+            if (warp + 1 < nwarps)
+                while (vprog[warp + 1] < i - MAS_RING + 1) {}  // the slot's previous tenant (row i − RING) has been read
+            vbnd[(i % MAS_RING) * 32 + warp] = cur;
+            __threadfence_block();
+            vprog[warp] = i;
+        }
+        issue(i + PF);
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every warp's direction words are visible to warp 0
+
+    if (warp == 0) {  // backtrack (alignment.py:62-73), 32 frames per step — as in mas_dp_kernel
+        int j = n_text - 1;
+        for (int top = n_mel - 1; top >= 1; top -= 32) {
+            const int row = top - lane;
+            const int wj = j >> 5;
+            uint32_t hi = 0, lo = 0;
+            if (row >= 1) {
+                hi = d[(size_t)row * W + wj];
+                if (wj > 0) lo = d[(size_t)row * W + wj - 1];
+            }
+            const int base = 32 * (wj - 1);
+            int myj = -1;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                if (top - r < 1) break;
+                const uint32_t h = __shfl_sync(0xffffffffu, hi, r);
+                const uint32_t l = __shfl_sync(0xffffffffu, lo, r);
+                if (lane == r) myj = j;
+                const int k = j - base;
+                const uint32_t bit = (k >= 32) ? ((h >> (k - 32)) & 1u) : ((l >> k) & 1u);
+                j -= (int)bit;
+            }
+            if (row >= 1) p[row] = myj;
+        }
+        if (lane == 0) p[0] = j;
+    }
+    __syncthreads();
+    for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
+}
+
 // log of the soft alignment (the `torch.log(attn.data)` of variance_adaptor.py:168) as a fully parallel
 // HBM-bound pass, so the sequential DP loop carries no transcendental
 __global__ void __launch_bounds__(256)
@@ -211,6 +321,13 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
 
 }  // namespace fs2k
 
+static int g_mas_wavefront = 1;
+// 1 (default): barrier-free wavefront kernel for T <= 1024; 0: one __syncthreads per frame (A/B measurements, tests)
+extern "C" int fs2k_mas_set_wavefront(int enabled) {
+    g_mas_wavefront = enabled ? 1 : 0;
+    return FS2K_OK;
+}
+
 static size_t mas_dirs_bytes(int B, int F, int T) {
     const size_t n = (size_t)B * F * ((T + 31) / 32) * sizeof(uint32_t);
     return (n + 255) / 256 * 256;
@@ -246,7 +363,15 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
     }
     cudaError_t e;
 #define MAS_ARGS B, threads, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations
-    if (chunks == 1) e = launch_mas<1, 16, false>(MAS_ARGS);
+    if (chunks == 1 && g_mas_wavefront) {
+        const size_t smem = (size_t)16 * threads * sizeof(float);
+        e = cudaSuccess;
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(mas_dp_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            fs2k_launch_serial(mas_dp_wave_kernel<16>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
+            e = cudaGetLastError();
+        }
+    } else if (chunks == 1) e = launch_mas<1, 16, false>(MAS_ARGS);
     else if (chunks == 2) e = launch_mas<2, 16, false>(MAS_ARGS);
     else { threads = 1024; e = launch_mas<4, 8, false>(MAS_ARGS); }
 #undef MAS_ARGS
