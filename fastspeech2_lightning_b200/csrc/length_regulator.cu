@@ -13,6 +13,16 @@
 
 namespace fs2k {
 
+// arg − 2π·rint(arg / 2π) for 0 ≤ arg < 5e4, to ≈ 1e-7: 2π = C1 + C2 + C3 with C1 (9 significant bits) and C2 chosen so
+// that k·C1 and k·C2 are exact in fp32 for k < 2^13
+__device__ __forceinline__ float posenc_reduce(float arg) {
+    const float k = rintf(arg * 0.15915494309189535f);
+    float r = fmaf(k, -6.28125f, arg);
+    r = fmaf(k, -1.9350051879882812e-3f, r);
+    r = fmaf(k, -3.0199160505556543e-7f, r);
+    return r;
+}
+
 // ---- scan: one warp per utterance, inclusive prefix sum of durations ----
 __global__ void __launch_bounds__(128)
 lr_scan_kernel(const int* __restrict__ dur, int B, int T, int* __restrict__ cum, int* __restrict__ total) {
@@ -98,14 +108,19 @@ lr_gather_kernel(const float* __restrict__ x,    // [B,T,D]
             if (dst) st_stream(dst + q, v);
             if (POS) {
                 if (idx >= 0) {
-                    // PositionalEmbedding (fs2/layers.py:132-140): [sin(f·ω_i) | cos(f·ω_i)], i < D/2
+                    // PositionalEmbedding (fs2/layers.py:132-140): [sin(f·ω_i) | cos(f·ω_i)], i < D/2.  The reference rounds the
+                    // product f·ω to fp32 first (a matmul of fp32 vectors) and takes sin / cos of THAT number — so does this:
+                    // no angle-addition recurrence.  sin / cos of the rounded argument: three-term Cody-Waite reduction by 2π
+                    // (exact for the ≤ 2^13 periods of positions up to 50 000) + the MUFU sine / cosine on [−π, π]
+                    // (abs error 4e-7): ≈ 10 instructions per channel instead of libdevice's ≈ 40.
                     const int half = D >> 1;
                     float e[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int ch = q * 4 + k;
                         const float arg = __fmul_rn((float)f, inv_freq[ch < half ? ch : ch - half]);
-                        e[k] = ch < half ? sinf(arg) : cosf(arg);
+                        const float r = posenc_reduce(arg);
+                        e[k] = ch < half ? __sinf(r) : __cosf(r);
                     }
                     v.x += e[0]; v.y += e[1]; v.z += e[2]; v.w += e[3];
                 }
