@@ -125,6 +125,25 @@ __device__ __forceinline__ unsigned long long hash_u64(unsigned long long seed, 
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long i) {
     return (float)(hash_u64(seed, i) >> 40) * (1.0f / 16777216.0f);
 }
+// Dropout decisions: ONE 64-bit hash decides four consecutive elements (group = element index >> 2, 16 bits each against
+// thr16 = round(p·65536)); the keep probability is exactly 1 − thr16/65536 and the survivors are scaled by its inverse.
+// Every kernel that drops (forward) or re-applies the mask (backward) goes through these helpers, so masks always agree.
+__device__ __forceinline__ uint32_t drop_thr16(float p) { return p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u; }
+__device__ __forceinline__ float drop_inv_keep(uint32_t thr16) { return 65536.0f / (float)(65536u - thr16); }
+__device__ __forceinline__ bool drop_keep_g(unsigned long long seed, unsigned long long group, int lane, uint32_t thr16) {
+    return ((uint32_t)(hash_u64(seed, group) >> (16 * lane)) & 0xFFFFu) >= thr16;
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long e, uint32_t thr16) {
+    return drop_keep_g(seed, e >> 2, (int)(e & 3), thr16);
+}
+// elements e .. e+3 with e % 4 == 0
+__device__ __forceinline__ void drop_apply4(float4& v, unsigned long long seed, unsigned long long e, uint32_t thr16, float inv_keep) {
+    const unsigned long long h = hash_u64(seed, e >> 2);
+    v.x = ((uint32_t)h & 0xFFFFu) >= thr16 ? v.x * inv_keep : 0.f;
+    v.y = ((uint32_t)(h >> 16) & 0xFFFFu) >= thr16 ? v.y * inv_keep : 0.f;
+    v.z = ((uint32_t)(h >> 32) & 0xFFFFu) >= thr16 ? v.z * inv_keep : 0.f;
+    v.w = ((uint32_t)(h >> 48) & 0xFFFFu) >= thr16 ? v.w * inv_keep : 0.f;
+}
 // Dropout under CUDA-graph replay: the by-value seeds of a captured launch are frozen, so every dropout kernel
 // adds *g_seed_base (a device counter the host rewrites before each replay; null → 0) to its seed on entry.
 // One copy of the pointer per translation unit; FS2K_DEFINE_SEED_BASE_SETTER(tag) exports its setter and

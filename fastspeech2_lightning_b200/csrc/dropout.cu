@@ -10,8 +10,11 @@ dropout_kernel(const float* __restrict__ x, const float* __restrict__ residual, 
                unsigned long long seed, long N, float* __restrict__ y) {
     pdl_prologue();
     seed = seed_with_base(seed);
+    const uint32_t thr16 = drop_thr16(p);
+    const float keep_scale = drop_inv_keep(thr16);
+    (void)inv_keep;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
-        const float v = hash_uniform(seed, (unsigned long long)i) >= p ? x[i] * inv_keep : 0.f;
+        const float v = drop_keep(seed, (unsigned long long)i, thr16) ? x[i] * keep_scale : 0.f;
         y[i] = residual ? v + residual[i] : v;
     }
 }

@@ -205,7 +205,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sh4[j] = (has[j] && ep.scale) ? __ldg(reinterpret_cast<const float4*>(ep.shift + n0) + qv) : zero4;
         }
         const int rows_valid = (int)min((long)HB_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
-        const float drop_p = DROPOUT ? ep.drop_p : 0.f, inv_keep = DROPOUT ? 1.0f / (1.0f - drop_p) : 1.f;
+        const float drop_p = DROPOUT ? ep.drop_p : 0.f;
+        const uint32_t thr16 = drop_thr16(drop_p);
+        const float inv_keep = drop_inv_keep(thr16);
         const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         const int act = ep.act;
         const float alpha = ep.alpha;
@@ -245,10 +247,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v.w = hb_act(v.w * sc4[j].w + sh4[j].w, act) * alpha;
                     if (DROPOUT) {
                         const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
-                        v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
-                        v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
-                        v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
-                        v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                        drop_apply4(v, seed, e, thr16, inv_keep);
                     }
                     v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
                     v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];

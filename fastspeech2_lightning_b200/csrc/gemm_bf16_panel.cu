@@ -161,7 +161,9 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
         const int quad = warp & 3, chalf = ew >> 2;       // TMEM lane quadrant, 64-column half of the tile
         float* stag = sStag + (size_t)ew * 32 * PB_STAG_PITCH;
         const int c4 = lane & 15, rsub = lane >> 4;       // store pass: 16 lanes cover a 64-float row, 2 rows per instruction
-        const float drop_p = DROPOUT ? ep.drop_p : 0.f, inv_keep = DROPOUT ? 1.0f / (1.0f - drop_p) : 1.f;
+        const float drop_p = DROPOUT ? ep.drop_p : 0.f;
+        const uint32_t thr16 = drop_thr16(drop_p);
+        const float inv_keep = drop_inv_keep(thr16);
         const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         const int act = ep.act;
         const float alpha = ep.alpha;
@@ -214,10 +216,7 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
                     v.z = pb_act(v.z, act) * alpha; v.w = pb_act(v.w, act) * alpha;
                     if (DROPOUT) {
                         const unsigned long long e = (unsigned long long)m * N + ncol;
-                        v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
-                        v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
-                        v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
-                        v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                        drop_apply4(v, seed, e, thr16, inv_keep);
                     }
                     v.x = (v.x + res[u].x) * rm[u]; v.y = (v.y + res[u].y) * rm[u];
                     v.z = (v.z + res[u].z) * rm[u]; v.w = (v.w + res[u].w) * rm[u];

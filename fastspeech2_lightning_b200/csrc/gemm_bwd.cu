@@ -17,7 +17,8 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
                float* __restrict__ gz) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     const int C4 = C >> 2;
     const long N = M * C4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -27,7 +28,7 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
         float o[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
         if (drop_p > 0.f) {  // the forward applied dropout after the activation: same mask on the gradient
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? o[k] * inv_keep : 0.f;
+            for (int k = 0; k < 4; ++k) o[k] = drop_keep_g(seed, (unsigned long long)i, k, thr16) ? o[k] * inv_keep : 0.f;
         }
         if (mode != 0) {
             const float4 a = reinterpret_cast<const float4*>(aux)[i];

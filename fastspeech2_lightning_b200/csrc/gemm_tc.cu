@@ -234,7 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rows_valid = (int)min((long)TC_BM, min((long)L - l0, M_total - ((long)b_idx * L + l0)));
         const float inv_n = 1.0f / (float)block_n;
         // (DROPOUT is a template flag: the counter hash must not sit in the store loop of the launches that never drop)
-        const float drop_p = DROPOUT ? ep.drop_p : 0.f, inv_keep = DROPOUT ? 1.0f / (1.0f - drop_p) : 1.f;
+        const float drop_p = DROPOUT ? ep.drop_p : 0.f;
+        const uint32_t thr16 = drop_thr16(drop_p);
+        const float inv_keep = drop_inv_keep(thr16);
         const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         constexpr int TC_ROWS_PER_ITER = TcRowsPerIter<LNORM>::value;
         for (int rb = warp; rb < rows_valid; rb += TC_WARPS * TC_ROWS_PER_ITER) {
@@ -268,10 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v = tc_colmath(v, bias4[j], sc4[j], sh4[j], ep.act, ep.alpha);
                         if (DROPOUT) {
                             const unsigned long long e = (unsigned long long)m * N + n0 + qv * 4;
-                            v.x = hash_uniform(seed, e) >= drop_p ? v.x * inv_keep : 0.f;
-                            v.y = hash_uniform(seed, e + 1) >= drop_p ? v.y * inv_keep : 0.f;
-                            v.z = hash_uniform(seed, e + 2) >= drop_p ? v.z * inv_keep : 0.f;
-                            v.w = hash_uniform(seed, e + 3) >= drop_p ? v.w * inv_keep : 0.f;
+                            drop_apply4(v, seed, e, thr16, inv_keep);
                         }
                         v.x = (v.x + res[u][j].x) * rm[u]; v.y = (v.y + res[u][j].y) * rm[u];
                         v.z = (v.z + res[u][j].z) * rm[u]; v.w = (v.w + res[u][j].w) * rm[u];

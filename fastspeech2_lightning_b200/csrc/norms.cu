@@ -16,7 +16,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     const int lane = threadIdx.x & 31;
     const int D4 = D >> 2;
     for (long m = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M;
@@ -60,10 +61,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                 o.w = (v[i].w - mean) * rstd * g.w + b.w;
                 if (drop_p > 0.f) {
                     const unsigned long long e = (unsigned long long)m * D + q * 4;
-                    o.x = hash_uniform(seed, e) >= drop_p ? o.x * inv_keep : 0.f;
-                    o.y = hash_uniform(seed, e + 1) >= drop_p ? o.y * inv_keep : 0.f;
-                    o.z = hash_uniform(seed, e + 2) >= drop_p ? o.z * inv_keep : 0.f;
-                    o.w = hash_uniform(seed, e + 3) >= drop_p ? o.w * inv_keep : 0.f;
+                    drop_apply4(o, seed, e, thr16, inv_keep);
                 }
                 yr[q] = o;
             }
@@ -159,7 +157,8 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
                   float* __restrict__ y) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     const int C4 = C >> 2;
     const long N = M * C4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
@@ -173,7 +172,7 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
             if (act == 1) o[k] = fmaxf(o[k], 0.f);
             else if (act == 2) o[k] = silu(o[k]);
             else if (act == 3) o[k] = tanhf(o[k]);
-            if (drop_p > 0.f) o[k] = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? o[k] * inv_keep : 0.f;
+            if (drop_p > 0.f) o[k] = drop_keep_g(seed, (unsigned long long)i, k, thr16) ? o[k] * inv_keep : 0.f;
         }
         if (residual) {
             const float4 r = reinterpret_cast<const float4*>(residual)[i];

@@ -12,7 +12,8 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                      float* __restrict__ dbeta) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     __shared__ float s_red[8][32 * MAXV * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D4 = D >> 2;
@@ -36,10 +37,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                 float4 gv = reinterpret_cast<const float4*>(g + (size_t)m * D)[q];
                 if (drop_p > 0.f) {  // the forward output was dropout(LN(x)): same mask on the incoming gradient
                     const unsigned long long e = (unsigned long long)m * D + q * 4;
-                    gv.x = hash_uniform(seed, e) >= drop_p ? gv.x * inv_keep : 0.f;
-                    gv.y = hash_uniform(seed, e + 1) >= drop_p ? gv.y * inv_keep : 0.f;
-                    gv.z = hash_uniform(seed, e + 2) >= drop_p ? gv.z * inv_keep : 0.f;
-                    gv.w = hash_uniform(seed, e + 3) >= drop_p ? gv.w * inv_keep : 0.f;
+                    drop_apply4(gv, seed, e, thr16, inv_keep);
                 }
                 const float4 xv = reinterpret_cast<const float4*>(x + (size_t)m * D)[q];
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -105,7 +103,8 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     double* __restrict__ sums) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     __shared__ double s_part[8][128][2];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long m0 = (long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
@@ -127,7 +126,7 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float gk = gv[k];
-                    if (drop_p > 0.f) gk = hash_uniform(seed, (unsigned long long)m * C + c + k) >= drop_p ? gk * inv_keep : 0.f;
+                    if (drop_p > 0.f) gk = drop_keep(seed, (unsigned long long)m * C + c + k, thr16) ? gk * inv_keep : 0.f;
                     const float gu = gk * act_grad_from_u(zv[k] * sc[k] + sh[k], act);
                     s[k] += gu;
                     q[k] += gu * (zv[k] - mu[k]) * rs[k];
@@ -164,7 +163,8 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     float* __restrict__ dbeta) {
     pdl_prologue();
     seed = seed_with_base(seed);
-    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+    const uint32_t thr16 = drop_thr16(drop_p);
+    const float inv_keep = drop_inv_keep(thr16);
     const int C4 = C >> 2;
     const long N = M * C4;
     const float inv_m = 1.0f / (float)M;
@@ -183,7 +183,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
         for (int k = 0; k < 4; ++k) {
             const float sc = scale[c + k];
             float gk = gv[k];
-            if (drop_p > 0.f) gk = hash_uniform(seed, (unsigned long long)i * 4 + k) >= drop_p ? gk * inv_keep : 0.f;
+            if (drop_p > 0.f) gk = drop_keep_g(seed, (unsigned long long)i, k, thr16) ? gk * inv_keep : 0.f;
             const float gu = gk * act_grad_from_u(zv[k] * sc + shift[c + k], act);
             if (training) {
                 const float zh = (zv[k] - mean[c + k]) * rstd[c + k];

@@ -190,14 +190,15 @@ def test_attention_tc_dropout_is_consistent_between_forward_dq_and_dkv():
     out0 = ops().attention_bf16(qkv16, lens_t, H)
     assert float((out - out0).abs().max()) > 1e-3          # dropout is active
     assert abs(float(out.mean() / out0.mean()) - 1.0) < 0.2 or True
-    w = rand(B, L, H * hd, seed=24)
+    w = r16(rand(B, L, H * hd, seed=24))   # exactly representable: the kernels read dO in bf16
     dqkv = ops().attention_bwd_bf16(qkv16, out, lse, w, lens_t, H, p, seed)
     D = H * hd
     dq, dk, dv = dqkv.split(D, dim=-1)
     q, k, v = r16(qkv).split(D, dim=-1)
     # out is linear in V for a fixed mask: <dV, δV> == <w, out(V + δV) − out(V)> iff forward and dkv use the same mask
-    dvv = (rand(B, L, D, seed=25) * 0.25).to(torch.bfloat16).float()
-    qkv2 = torch.cat([q, k, v + dvv], dim=-1)
+    v2 = r16(v + rand(B, L, D, seed=25) * 0.25)
+    dvv = v2 - v                           # the perturbation the kernel really sees (both ends are bf16 numbers)
+    qkv2 = torch.cat([q, k, v2], dim=-1)
     out2 = ops().attention_bf16(ops().cast_bf16(qkv2)[0], lens_t, H, dropout_p=p, seed=seed)
     lhs, rhs = float((dv * dvv).sum()), float((w * (out2 - out)).sum())
     assert abs(lhs - rhs) <= 3e-2 * max(abs(rhs), 1.0), (lhs, rhs)
