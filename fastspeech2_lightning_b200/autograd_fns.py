@@ -261,6 +261,84 @@ def conv1d_bn_act(x, weight, bias, bn, act, training, dropout_p=0.0):
     return _ConvBnAct.apply(x.contiguous(), weight, bias, bn.weight, bn.bias, bn, act, training, float(dropout_p))
 
 
+class _PostNetBf16(torch.autograd.Function):
+    """PostNet (fs2/layers.py:143-212: 5 × [Conv1d k5 → BatchNorm1d → tanh (not on the last) → Dropout 0.5]) in the bf16 mode
+    as ONE autograd node.  Between the layers the activations exist only in bf16 (written by the BatchNorm-affine + tanh
+    + dropout kernel, read by the next convolution's TMA), and in the backward the BatchNorm/tanh gradient gz exists only in
+    bf16 (read by TMA in both the data-gradient and the weight-gradient contraction): the five k = 5, 512-channel
+    convolutions — the compute-bound third of the model — run TMA-fed in all three directions."""
+
+    @staticmethod
+    def forward(ctx, x, training, p_drop, bns, *params):
+        n = len(bns)
+        h = x
+        saved, meta = [], []
+        for i in range(n):
+            weight, bias = params[4 * i], params[4 * i + 1]
+            w_taps = ops.conv_weight_taps(weight)
+            taps, N, K = w_taps.shape
+            pad = (taps - 1) // 2
+            w16, _ = ops.bf16_weight(w_taps)
+            hint = 256 if (taps * K >= 1024 and N % 256 == 0) else 0
+            z, _, _ = ops.gemm_bf16(h, w16, bias.detach() if bias is not None else None, taps_pad=pad, block_n_hint=hint)
+            scale, shift, mean, rstd = ops.bn_scale_shift(bns[i], z, training, save_stats=True)
+            seed = _seed(p_drop)
+            act = "tanh" if i < n - 1 else None
+            saved += [h, w16, z, scale, shift, mean, rstd]
+            meta.append((act, pad, seed, hint, bias is not None))
+            if i < n - 1:
+                h = ops.affine_act(z, scale, shift, act, None, p_drop, seed, out_bf16=True)
+            else:
+                out = ops.affine_act(z, scale, shift, act, None, p_drop, seed)
+        ctx.save_for_backward(*saved)
+        ctx.meta, ctx.cfg, ctx.params = meta, (training, p_drop, n), params
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        training, p_drop, n = ctx.cfg
+        saved, params = ctx.saved_tensors, ctx.params
+        grads = [None] * (4 * n)
+        g = g.contiguous()
+        sink = _SINK
+        for i in range(n - 1, -1, -1):
+            h, w16, z, scale, shift, mean, rstd = saved[7 * i: 7 * i + 7]
+            act, pad, seed, hint, has_bias = ctx.meta[i]
+            weight, bias, bn_w, bn_b = params[4 * i: 4 * i + 4]
+            taps = w16.shape[0]
+            direct_bn = _direct_grads(bn_w, bn_b)
+            gz16, dgamma, dbeta = ops.bn_act_bwd(g, z, scale, shift, mean, rstd, act, training, p_drop, seed,
+                                                 accumulate_into=direct_bn, out_bf16=True)
+            if direct_bn is None:
+                grads[4 * i + 2], grads[4 * i + 3] = dgamma, dbeta
+            direct_w = _direct_grads(weight, bias) if has_bias else _direct_grads(weight)
+            if sink is not None and direct_w is not None:
+                sink.stream.wait_stream(torch.cuda.current_stream())
+                sink.keep.append((gz16, h))
+                with torch.cuda.stream(sink.stream):
+                    if has_bias:
+                        ops.colsum(gz16, out=bias.grad, accumulate=True)
+                    ops.gemm_wgrad_bf16(gz16, h, taps, pad, True, accumulate_into=weight.grad)
+            else:
+                if has_bias:
+                    grads[4 * i + 1] = ops.colsum(gz16)
+                grads[4 * i] = ops.gemm_wgrad_bf16(gz16, h, taps, pad, True)
+            if i > 0 or ctx.needs_input_grad[0]:
+                g, _, _ = ops.gemm_bf16(gz16, w16, None, w_mn=True, taps_pad=taps - 1 - pad, block_n_hint=hint)
+        return (g if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+
+
+def postnet_bf16(x, pn, training, dropout_p):
+    params = []
+    bns = []
+    for block in pn.convolutions:
+        conv, bn = block[0].conv, block[1]
+        params += [conv.weight, conv.bias, bn.weight, bn.bias]
+        bns.append(bn)
+    return _PostNetBf16.apply(x.contiguous(), bool(training), float(dropout_p), bns, *params)
+
+
 class _GluDwconvBnSilu(torch.autograd.Function):
     """GLU → depthwise conv → BatchNorm1d → SiLU (torchaudio conformer.py:50-65)."""
 

@@ -171,6 +171,23 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
             const int buf = jj & 1;
             const int ncol = (j_begin + jj) * PB_BN + chalf * 64 + c4 * 4;   // this lane's 4 output columns
             const float4 bias4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // software-pipelined global reads: trip t+1's residual rows / row masks are in flight while trip t is processed,
+            // and trip 0's are issued before the wait for the accumulator
+            float4 res_n[4];
+            float rm_n[4];
+            auto load_trip = [&](int rb) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long m = m0 + quad * 32 + rb + u * 2 + rsub;
+                    res_n[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rm_n[u] = 1.f;
+                    if (m < M) {
+                        if (ep.residual) res_n[u] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + ncol);
+                        if (ep.row_mask) rm_n[u] = ep.row_mask[m] ? 1.f : 0.f;
+                    }
+                }
+            };
+            load_trip(0);
             mbar_wait(smem_u32(&s_tmem_full[buf]), (jj >> 1) & 1);
             tc_fence_after();
             {
@@ -188,21 +205,14 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[buf])) : "memory");
-            // rows of this warp: quad*32 + [0,32); 4 row pairs per trip, their global reads issued first
+            // rows of this warp: quad*32 + [0,32); 4 row pairs per trip
 #pragma unroll 1
             for (int rb = 0; rb < 32; rb += 8) {
                 float4 res[4];
                 float rm[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long m = m0 + quad * 32 + rb + u * 2 + rsub;
-                    res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    rm[u] = 1.f;
-                    if (m < M) {
-                        if (ep.residual) res[u] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + ncol);
-                        if (ep.row_mask) rm[u] = ep.row_mask[m] ? 1.f : 0.f;
-                    }
-                }
+                for (int u = 0; u < 4; ++u) { res[u] = res_n[u]; rm[u] = rm_n[u]; }
+                if (rb + 8 < 32) load_trip(rb + 8);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int r = rb + u * 2 + rsub;

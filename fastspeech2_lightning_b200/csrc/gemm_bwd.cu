@@ -6,6 +6,8 @@
 //             dx = conv_transpose(gz, W)                           forward GEMM on the flipped/transposed taps
 //                                                                  (fs2k_repack_weight_t builds them)
 //             dW[tap][n][k] = Σ_(b,l) gz[b,l,n]·x[b,l+tap−pad,k]   fs2k_gemm_wgrad  (reduction over rows)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fs2k {
@@ -48,8 +50,11 @@ act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ aux, int m
 
 // out[c] += Σ_m z[m,c]   (out zeroed by the launcher unless it accumulates; fp32 partials per CTA, one atomic per
 // column per CTA; blockIdx.y selects the 128-channel block, blockIdx.x the row chunk)
+template <bool IN16>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, float* __restrict__ out) {
+colsum_kernel(const void* __restrict__ zv, long M, int C, long rows_per_cta, float* __restrict__ out) {
+    const float* z = reinterpret_cast<const float*>(zv);
+    const __nv_bfloat16* z16 = reinterpret_cast<const __nv_bfloat16*>(zv);
     pdl_prologue();
     __shared__ float s_part[8][128];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -61,7 +66,15 @@ colsum_kernel(const float* __restrict__ z, long M, int C, long rows_per_cta, flo
         if (c < C)
 #pragma unroll 4
             for (long m = m0 + grp; m < m1; m += 8) {
-                const float4 v = *reinterpret_cast<const float4*>(z + (size_t)m * C + c);
+                float4 v;
+                if (IN16) {
+                    const uint2 pk = *reinterpret_cast<const uint2*>(z16 + (size_t)m * C + c);
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+                    v = make_float4(a.x, a.y, b.x, b.y);
+                } else {
+                    v = *reinterpret_cast<const float4*>(z + (size_t)m * C + c);
+                }
                 s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
             }
 #pragma unroll
@@ -198,7 +211,24 @@ extern "C" int fs2k_colsum(const float* z, long M, int C, float* out, int accumu
     if (M == 0) return FS2K_OK;
     long rows;
     const dim3 grid = col_reduce_grid(M, C, &rows);
-    fs2k_launch(colsum_kernel, dim3(grid), dim3(256), 0, s, z, M, C, rows, out);
+    fs2k_launch(colsum_kernel<false>, dim3(grid), dim3(256), 0, s, (const void*)z, M, C, rows, out);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+extern "C" int fs2k_colsum_bf16(const void* z_bf16, long M, int C, float* out, int accumulate, fs2k_stream_t stream) {
+    FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
+    FS2K_REQUIRE((C & 3) == 0, FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE(out && (z_bf16 || M == 0), FS2K_ERR_NULL);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * C, s);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    }
+    if (M == 0) return FS2K_OK;
+    long rows;
+    const dim3 grid = col_reduce_grid(M, C, &rows);
+    fs2k_launch(colsum_kernel<true>, dim3(grid), dim3(256), 0, s, z_bf16, M, C, rows, out);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -11,6 +11,8 @@
 // accumulate in fp32 in TMEM.  The row range is split over CTAs; partial tiles go to a workspace that
 // wgrad_reduce_kernel (gemm_wgrad_tc.cu) sums in a fixed order.  N and K need not be multiples of the tile: the
 // 80-channel mel projections run here too (rows / columns past the edge are zero-filled and never written).
+#include <cstring>
+
 #include "bf16_common.cuh"
 
 namespace fs2k {
@@ -21,8 +23,12 @@ constexpr int WB_THREADS = 384;
 constexpr int WB_CONV_THREADS = 256;
 constexpr int WB_STAGES = 4;
 
+// G16 / X16: that operand is bf16 in HBM and comes in by TMA (boxes of 64 columns × 64 rows of a 3-D map [B][L][C],
+// rows outside the utterance zero-filled) instead of through the converting producer warps.
+template <bool G16, bool X16>
 __global__ void __launch_bounds__(WB_THREADS, 1)
-gemm_wgrad_bf16_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, int L, int N, int K,
+gemm_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                       const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, int L, int N, int K,
                        int tile_k, int taps, int pad, int chunks_per_b, int n_chunks, int chunks_per_split,
                        float* __restrict__ ws) {
     pdl_launch_dependents();
@@ -41,7 +47,7 @@ gemm_wgrad_bf16_kernel(const float* __restrict__ G, int ldg, const float* __rest
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < WB_STAGES; ++s) {
-            mbar_init(smem_u32(&s_full[s]), WB_CONV_THREADS);
+            mbar_init(smem_u32(&s_full[s]), ((G16 && X16) ? 0 : WB_CONV_THREADS) + ((G16 || X16) ? 1 : 0));
             mbar_init(smem_u32(&s_empty[s]), 1);
         }
         mbar_init(smem_u32(&s_tmem_full), 1);
@@ -57,7 +63,24 @@ gemm_wgrad_bf16_kernel(const float* __restrict__ G, int ldg, const float* __rest
     const uint32_t tmem_base = s_tmem_base;
     pdl_wait();
 
-    if (warp == 1) {
+    if (warp == 0) {
+        if ((G16 || X16) && lane == 0) {
+            // ================= TMA producer for the bf16 operand(s) =================
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % WB_STAGES, ph = (it / WB_STAGES) & 1;
+                mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+                const int c = c_begin + it;
+                const int b = c / chunks_per_b, l0 = (c % chunks_per_b) * WB_ROWS;
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+                const uint32_t bar = smem_u32(&s_full[s]);
+                mbar_expect_tx(bar, (G16 ? a_bytes : 0u) + (X16 ? b_bytes : 0u));
+                if (G16)
+                    for (int j = 0; j < WB_N / 64; ++j) tma_load_3d(sa + j * 8192, &tmG, bar, n0 + 64 * j, l0, b);
+                if (X16)
+                    for (int j = 0; j * 64 < tile_k; ++j) tma_load_3d(sb + j * 8192, &tmX, bar, k0 + 64 * j, l0 + tap - pad, b);
+            }
+        }
+    } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = hb_idesc(tile_k, 1, 1);  // both operands MN-major
             for (int it = 0; it < iters; ++it) {
@@ -79,31 +102,37 @@ gemm_wgrad_bf16_kernel(const float* __restrict__ G, int ldg, const float* __rest
         const int x_c4 = ct & 63, x_r = ct >> 6;           // X: up to 64 float4 per row, 4 rows per pass
         const bool g_col_ok = n0 + g_c4 * 4 < N;
         const bool x_col_ok = x_c4 * 4 < tile_k && k0 + x_c4 * 4 < K;
-        for (int it = 0; it < iters; ++it) {
+        for (int it = 0; it < ((G16 && X16) ? 0 : iters); ++it) {
             const int s = it % WB_STAGES, ph = (it / WB_STAGES) & 1;
             const int c = c_begin + it;
             const int b = c / chunks_per_b, l0 = (c % chunks_per_b) * WB_ROWS;
             float4 gv[8], xv[16];
+            if (!G16) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int l = l0 + p * 8 + g_r;
-                gv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g_col_ok && l < L) gv[p] = ld_stream(reinterpret_cast<const float4*>(G + ((size_t)b * L + l) * ldg + n0 + g_c4 * 4));
+                for (int p = 0; p < 8; ++p) {
+                    const int l = l0 + p * 8 + g_r;
+                    gv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g_col_ok && l < L) gv[p] = ld_stream(reinterpret_cast<const float4*>(G + ((size_t)b * L + l) * ldg + n0 + g_c4 * 4));
+                }
             }
+            if (!X16) {
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                const int l = l0 + p * 4 + x_r, lx = l + tap - pad;
-                xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (x_col_ok && l < L && lx >= 0 && lx < L)
-                    xv[p] = ld_stream(reinterpret_cast<const float4*>(X + ((size_t)b * L + lx) * ldx + k0 + x_c4 * 4));
+                for (int p = 0; p < 16; ++p) {
+                    const int l = l0 + p * 4 + x_r, lx = l + tap - pad;
+                    xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (x_col_ok && l < L && lx >= 0 && lx < L)
+                        xv[p] = ld_stream(reinterpret_cast<const float4*>(X + ((size_t)b * L + lx) * ldx + k0 + x_c4 * 4));
+                }
             }
             mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             uint8_t* sb = sa + a_bytes;
+            if (!G16) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p)
-                *reinterpret_cast<uint2*>(sa + hb_tile_off(p * 8 + g_r, g_c4 * 4, 8192)) = hb_pack4(gv[p]);
-            if (x_c4 * 4 < tile_k) {
+                for (int p = 0; p < 8; ++p)
+                    *reinterpret_cast<uint2*>(sa + hb_tile_off(p * 8 + g_r, g_c4 * 4, 8192)) = hb_pack4(gv[p]);
+            }
+            if (!X16 && x_c4 * 4 < tile_k) {
 #pragma unroll
                 for (int p = 0; p < 16; ++p)
                     *reinterpret_cast<uint2*>(sb + hb_tile_off(p * 4 + x_r, x_c4 * 4, 8192)) = hb_pack4(xv[p]);
@@ -172,11 +201,23 @@ extern "C" size_t fs2k_gemm_wgrad_bf16_workspace_bytes(int B, int L, int N, int 
     return (size_t)splits * taps * N * K * sizeof(float);
 }
 
-extern "C" int fs2k_gemm_wgrad_bf16(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps,
-                                    int pad, void* workspace, size_t workspace_bytes, float* dW_param_layout, int accumulate,
-                                    fs2k_stream_t stream) {
+static bool wb_make_map(CUtensorMap* tm, const void* base, int cols, int ld, int L, int B) {
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+    cuuint32_t box[3] = {64, WB_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+extern "C" int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, const void* X, int x_is_bf16, int ldx, int B, int L,
+                                       int N, int K, int taps, int pad, void* workspace, size_t workspace_bytes,
+                                       float* dW_param_layout, int accumulate, fs2k_stream_t stream) {
     FS2K_REQUIRE(B > 0 && L > 0 && N > 0 && K > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(fs2k_gemm_wgrad_bf16_supported(N, K, ldg, ldx), FS2K_ERR_UNSUPPORTED);
+    FS2K_REQUIRE((!g_is_bf16 || (ldg % 8) == 0) && (!x_is_bf16 || (ldx % 8) == 0), FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(G && X && workspace && dW_param_layout, FS2K_ERR_NULL);
     FS2K_REQUIRE(workspace_bytes >= fs2k_gemm_wgrad_bf16_workspace_bytes(B, L, N, K, taps), FS2K_ERR_WORKSPACE);
     int tile_k, splits, cps;
@@ -184,18 +225,36 @@ extern "C" int fs2k_gemm_wgrad_bf16(const float* G, int ldg, const float* X, int
     const int chunks_per_b = (L + WB_ROWS - 1) / WB_ROWS;
     const int n_chunks = B * chunks_per_b;
     FS2K_REQUIRE((long)splits * taps <= 65535, FS2K_ERR_UNSUPPORTED);
+    CUtensorMap tmG, tmX;
+    memset(&tmG, 0, sizeof(tmG));
+    memset(&tmX, 0, sizeof(tmX));
+    if (g_is_bf16 && !wb_make_map(&tmG, G, N, ldg, L, B)) return fs2k_set_cuda_error(cudaErrorInvalidValue);
+    if (x_is_bf16 && !wb_make_map(&tmX, X, K, ldx, L, B)) return fs2k_set_cuda_error(cudaErrorInvalidValue);
     const size_t stage = (size_t)(WB_N / 64) * 8192 + (size_t)((tile_k + 63) / 64) * 8192;
     const size_t smem = stage * WB_STAGES + 1024;
     FS2K_REQUIRE(smem <= 227 * 1024, FS2K_ERR_UNSUPPORTED);
     dim3 grid((N + WB_N - 1) / WB_N, K / tile_k, (unsigned)(splits * taps));
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    auto launch = [&](auto kernel) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return;
+        fs2k_launch(kernel, dim3(grid), dim3(WB_THREADS), smem, s, tmG, tmX, g_is_bf16 ? nullptr : (const float*)G, ldg,
+                    x_is_bf16 ? nullptr : (const float*)X, ldx, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+    };
+    if (g_is_bf16 && x_is_bf16) launch(gemm_wgrad_bf16_kernel<true, true>);
+    else if (g_is_bf16) launch(gemm_wgrad_bf16_kernel<true, false>);
+    else if (x_is_bf16) launch(gemm_wgrad_bf16_kernel<false, true>);
+    else launch(gemm_wgrad_bf16_kernel<false, false>);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-    fs2k_launch(gemm_wgrad_bf16_kernel, dim3(grid), dim3(WB_THREADS), smem, s, G, ldg, X, ldx, L, N, K, tile_k, taps, pad,
-                chunks_per_b, n_chunks, cps, (float*)workspace);
     FS2K_CHECK_LAUNCH();
-    FS2K_REQUIRE(((long)N * K) % 4 == 0, FS2K_ERR_UNSUPPORTED);
     wgrad_reduce_launch((const float*)workspace, splits, taps, N, K, accumulate, dW_param_layout, s);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
+}
+
+extern "C" int fs2k_gemm_wgrad_bf16(const float* G, int ldg, const float* X, int ldx, int B, int L, int N, int K, int taps,
+                                    int pad, void* workspace, size_t workspace_bytes, float* dW_param_layout, int accumulate,
+                                    fs2k_stream_t stream) {
+    return fs2k_gemm_wgrad_bf16_ex(G, 0, ldg, X, 0, ldx, B, L, N, K, taps, pad, workspace, workspace_bytes, dW_param_layout, accumulate, stream);
 }

@@ -4,6 +4,8 @@
 //   BatchNorm1d                torchaudio conformer.py:62-64 ; fs2/layers.py:168-202
 // BatchNorm in training mode uses the biased variance of all B·L positions including padding
 // (SURVEY §8a note P) and updates running stats with momentum 0.1 and the unbiased variance.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fs2k {
@@ -151,10 +153,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long M, int 
 }
 
 // y = act(z·scale[c] + shift[c]) (+ residual)    act: 0 none, 1 relu, 2 silu, 3 tanh
+template <bool OUT16>
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   int act, const float* __restrict__ residual, long M, int C, float drop_p, unsigned long long seed,
-                  float* __restrict__ y) {
+                  void* __restrict__ y) {
     pdl_prologue();
     seed = seed_with_base(seed);
     const uint32_t thr16 = drop_thr16(drop_p);
@@ -178,7 +181,15 @@ affine_act_kernel(const float* __restrict__ z, const float* __restrict__ scale, 
             const float4 r = reinterpret_cast<const float4*>(residual)[i];
             o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
         }
-        reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (OUT16) {  // bf16 mode: the value only feeds a tensor-core contraction (its TMA reads bf16 tiles)
+            const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&a);
+            pk.y = *reinterpret_cast<const uint32_t*>(&b);
+            reinterpret_cast<uint2*>(y)[i] = pk;
+        } else {
+            reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -242,8 +253,22 @@ extern "C" int fs2k_affine_act(const float* z, const float* scale, const float* 
     FS2K_REQUIRE(z && y && (!scale || shift), FS2K_ERR_NULL);  // scale == NULL: plain activation
     long g = (M * (C >> 2) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    fs2k_launch(affine_act_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, z, scale, shift, act, residual, M, C, dropout_p,
-                                                                (unsigned long long)seed, y);
+    fs2k_launch(affine_act_kernel<false>, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, z, scale, shift, act, residual, M, C, dropout_p,
+                                                                (unsigned long long)seed, (void*)y);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
+
+extern "C" int fs2k_affine_act_bf16(const float* z, const float* scale, const float* shift, int act, const float* residual,
+                                    long M, int C, float dropout_p, long seed, void* y_bf16, fs2k_stream_t stream) {
+    FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
+    FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
+    if (M == 0) return FS2K_OK;
+    FS2K_REQUIRE(z && y_bf16 && (!scale || shift), FS2K_ERR_NULL);
+    long g = (M * (C >> 2) + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    fs2k_launch(affine_act_kernel<true>, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, z, scale, shift, act, residual, M, C, dropout_p,
+                                                                (unsigned long long)seed, y_bf16);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
 }

@@ -1,4 +1,6 @@
 // Backward of LayerNorm and of BatchNorm1d (+ fused activation).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fs2k {
@@ -155,11 +157,12 @@ bn_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 }
 
 // training: gz = γ·rstd·(gu − Σgu/M − ẑ·Σ(gu·ẑ)/M) ; eval: gz = gu·scale.   dγ = Σ gu·ẑ, dβ = Σ gu (written by block 0)
+template <bool OUT16>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const double* __restrict__ sums, int act, int training, long M, int C, float drop_p,
-                    unsigned long long seed, int accumulate, float* __restrict__ gz, float* __restrict__ dgamma,
+                    unsigned long long seed, int accumulate, void* __restrict__ gz, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
     pdl_prologue();
     seed = seed_with_base(seed);
@@ -192,7 +195,15 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                 o[k] = gu * sc;
             }
         }
-        reinterpret_cast<float4*>(gz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (OUT16) {  // bf16 mode: gz only feeds the data- and weight-gradient contractions
+            const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&a);
+            pk.y = *reinterpret_cast<const uint32_t*>(&b);
+            reinterpret_cast<uint2*>(gz)[i] = pk;
+        } else {
+            reinterpret_cast<float4*>(gz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -227,10 +238,10 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
     return FS2K_OK;
 }
 
-extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift,
-                               const float* mean, const float* rstd, int act, int training, long M, int C,
-                               float dropout_p, long seed, double* sums /* [2C] scratch */, float* gz, float* dgamma,
-                               float* dbeta, int accumulate, fs2k_stream_t stream) {
+static int bn_act_bwd_impl(const float* g, const float* z, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, int act, int training, long M, int C,
+                           float dropout_p, long seed, double* sums, void* gz, int gz_bf16, float* dgamma,
+                           float* dbeta, int accumulate, fs2k_stream_t stream) {
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && C > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((C & 3) == 0 && act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
@@ -245,9 +256,26 @@ extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scal
     FS2K_CHECK_LAUNCH();
     long grid = (M * (C >> 2) + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    fs2k_launch(bn_bwd_apply_kernel, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, accumulate, gz, dgamma, dbeta);
+    if (gz_bf16)
+        fs2k_launch(bn_bwd_apply_kernel<true>, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, accumulate, gz, dgamma, dbeta);
+    else
+        fs2k_launch(bn_bwd_apply_kernel<false>, dim3((int)grid), dim3(256), 0, s, g, z, scale, shift, mean, rstd, sums, act, training, M, C, dropout_p, useed, accumulate, gz, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
+}
+
+extern "C" int fs2k_bn_act_bwd(const float* g, const float* z, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, int act, int training, long M, int C,
+                               float dropout_p, long seed, double* sums /* [2C] scratch */, float* gz, float* dgamma,
+                               float* dbeta, int accumulate, fs2k_stream_t stream) {
+    return bn_act_bwd_impl(g, z, scale, shift, mean, rstd, act, training, M, C, dropout_p, seed, sums, gz, 0, dgamma, dbeta, accumulate, stream);
+}
+
+extern "C" int fs2k_bn_act_bwd_bf16(const float* g, const float* z, const float* scale, const float* shift,
+                                    const float* mean, const float* rstd, int act, int training, long M, int C,
+                                    float dropout_p, long seed, double* sums, void* gz_bf16, float* dgamma,
+                                    float* dbeta, int accumulate, fs2k_stream_t stream) {
+    return bn_act_bwd_impl(g, z, scale, shift, mean, rstd, act, training, M, C, dropout_p, seed, sums, gz_bf16, 1, dgamma, dbeta, accumulate, stream);
 }
 
 FS2K_DEFINE_SEED_BASE_SETTER(norms_bwd)

@@ -75,12 +75,44 @@ def variance_predictor(x, mask, vp, training: bool):
 # PostNet  (fs2/layers.py:143-212)
 # ---------------------------------------------------------------------------------------------
 def postnet(x, pn, training: bool):
+    from . import ops
+
     n = len(pn.convolutions)
+    p_drop = 0.5 if training and pn.dropout_in_training else 0.0
+    if ops.PRECISION == "bf16" and _postnet_bf16_ok(pn, x):
+        if ag._needs_grad(x, *pn.parameters()) or p_drop > 0.0 or training:
+            from . import autograd_fns as fns
+
+            return fns.postnet_bf16(x, pn, training, p_drop)
+        # synthesis: BatchNorm folded into the convolution's epilogue, bf16 activations between the layers
+        h = x.detach()
+        for i, block in enumerate(pn.convolutions):
+            conv, bn = block[0].conv, block[1]
+            w_taps = ops.conv_weight_taps(conv.weight)
+            taps, N, K = w_taps.shape
+            w16, _ = ops.bf16_weight(w_taps)
+            scale, shift = ops.bn_scale_shift(bn, None, False)
+            last = i == n - 1
+            c, c16, _ = ops.gemm_bf16(h, w16, conv.bias, taps_pad=(taps - 1) // 2, scale=scale, shift=shift, act=None if last else "tanh",
+                                      want_c=last, want_c16=not last, block_n_hint=256 if (taps * K >= 1024 and N % 256 == 0) else 0)
+            h = c if last else c16
+        return h
     for i, block in enumerate(pn.convolutions):
         conv, bn = block[0].conv, block[1]
         act = "tanh" if i < n - 1 else None
-        x = ag.conv1d_bn_act(x, conv.weight, conv.bias, bn, act, training, dropout=0.5 if training and pn.dropout_in_training else 0.0)
+        x = ag.conv1d_bn_act(x, conv.weight, conv.bias, bn, act, training, dropout=p_drop)
     return x
+
+
+def _postnet_bf16_ok(pn, x) -> bool:
+    """Every layer's shapes are taken by the TMA-fed bf16 kernels (channels multiples of 16: 80 / 512 in the base config)."""
+    if not x.is_cuda or x.dim() != 3:
+        return False
+    for block in pn.convolutions:
+        w = block[0].conv.weight
+        if w.shape[0] % 16 or w.shape[1] % 16 or (w.shape[0] > 256 and w.shape[0] % 128):
+            return False
+    return True
 
 
 # ---------------------------------------------------------------------------------------------

@@ -238,10 +238,16 @@ def bn_scale_shift(bn: torch.nn.modules.batchnorm._BatchNorm, z: Optional[torch.
     return scale, shift
 
 
-def affine_act(z, scale, shift, act=None, residual=None, dropout_p: float = 0.0, seed: int = 0):
+def affine_act(z, scale, shift, act=None, residual=None, dropout_p: float = 0.0, seed: int = 0, out_bf16: bool = False):
     z = _f32(z, "z")
     C = z.shape[-1]
     M = z.numel() // C
+    if out_bf16:  # the value only feeds a bf16-mode contraction: rounded here, the fp32 copy is never written
+        y = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device)
+        check(lib().fs2k_affine_act_bf16(_p(z), _p(scale), _p(shift), _ACTS[act], _p(residual), M, C, float(dropout_p), int(seed), _p(y), _stream()),
+              "fs2k_affine_act_bf16")
+        _count()
+        return y
     y = torch.empty_like(z)
     check(lib().fs2k_affine_act(_p(z), _p(scale), _p(shift), _ACTS[act], _p(residual), M, C, float(dropout_p), int(seed), _p(y), _stream()), "fs2k_affine_act")
     _count()
@@ -648,23 +654,33 @@ def gemm_bf16(a, w_hi, bias=None, *, w_lo=None, w_mn: bool = False, taps_pad: in
     return c, c16, pre
 
 
+def _f32_or_bf16(t, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype == torch.bfloat16:
+        return t if t.is_contiguous() else t.contiguous()
+    return _f32(t, name)
+
+
 def gemm_wgrad_bf16(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=None):
-    """bf16-mode weight gradient: g [B,L,N], x [B,L,K] fp32 → [N,K,taps] (conv_layout) or [N,K]; None when unsupported."""
-    g, x = _f32(g, "g"), _f32(x, "x")
+    """bf16-mode weight gradient: g [B,L,N], x [B,L,K] (each fp32 — rounded in the kernel — or bf16 — read by TMA) →
+    [N,K,taps] (conv_layout) or [N,K]; None when the shape is not taken."""
+    g, x = _f32_or_bf16(g, "g"), _f32_or_bf16(x, "x")
     if g.dim() == 2:
         B, L = 1, g.shape[0]
     else:
         B, L = g.shape[0], g.shape[1]
     N, K = g.shape[-1], x.shape[-1]
-    if B * L == 0 or not lib().fs2k_gemm_wgrad_bf16_supported(N, K, N, K):
+    g16, x16 = g.dtype == torch.bfloat16, x.dtype == torch.bfloat16
+    if B * L == 0 or not lib().fs2k_gemm_wgrad_bf16_supported(N, K, N, K) or (g16 and N % 8) or (x16 and K % 8):
         return None
     ws_bytes = lib().fs2k_gemm_wgrad_bf16_workspace_bytes(B, L, N, K, taps)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
     acc = accumulate_into is not None and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
     out = accumulate_into if acc else torch.empty((N, K, taps) if conv_layout else (N, K), dtype=torch.float32, device=g.device)
     assert out.numel() == N * K * taps
-    check(lib().fs2k_gemm_wgrad_bf16(_p(g), N, _p(x), K, B, L, N, K, taps, pad, _p(ws), ws_bytes, _p(out), int(acc), _stream()),
-          "fs2k_gemm_wgrad_bf16")
+    check(lib().fs2k_gemm_wgrad_bf16_ex(_p(g), int(g16), N, _p(x), int(x16), K, B, L, N, K, taps, pad, _p(ws), ws_bytes, _p(out), int(acc),
+                                        _stream()), "fs2k_gemm_wgrad_bf16_ex")
     _count(2)
     if accumulate_into is not None and not acc:
         accumulate_into.add_(out)
@@ -993,11 +1009,15 @@ def act_bwd(g, aux, act, alpha: float = 1.0, row_mask=None, dropout_p: float = 0
 
 def colsum(z, out=None, accumulate: bool = False):
     """out[c] (+)= Σ_m z[m,c]  (bias gradients); `out` + `accumulate` add straight into an existing gradient."""
-    z = _f32(z, "z")
+    z = _f32_or_bf16(z, "z")
     C = z.shape[-1]
     if out is None:
         out, accumulate = torch.empty((C,), dtype=torch.float32, device=z.device), False
     assert out.is_contiguous() and out.numel() == C and out.dtype == torch.float32
+    if z.dtype == torch.bfloat16:
+        check(lib().fs2k_colsum_bf16(_p(z), z.numel() // C, C, _p(out), int(accumulate), _stream()), "fs2k_colsum_bf16")
+        _count()
+        return out
     check(lib().fs2k_colsum(_p(z), z.numel() // C, C, _p(out), int(accumulate), _stream()), "fs2k_colsum")
     _count()
     return out
@@ -1016,7 +1036,7 @@ def weight_taps_transposed(w_taps):
 def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=None):
     """dW for y = conv(x, W): g [B,L,N], x [B,L,K] → [N,K,taps] (conv_layout) or [N,K].  `accumulate_into` (a
     contiguous fp32 tensor of that shape, e.g. the parameter's .grad) receives `+= dW` instead of a new tensor."""
-    g, x = _f32(g, "g"), _f32(x, "x")
+    g, x = _f32_or_bf16(g, "g"), _f32_or_bf16(x, "x")
     if g.dim() == 2:
         B, L = 1, g.shape[0]
     else:
@@ -1026,6 +1046,8 @@ def gemm_wgrad(g, x, taps: int, pad: int, conv_layout: bool, accumulate_into=Non
         out = gemm_wgrad_bf16(g, x, taps, pad, conv_layout, accumulate_into)
         if out is not None:
             return out
+        if g.dtype == torch.bfloat16 or x.dtype == torch.bfloat16:
+            g, x = g.float(), x.float()
     if PRECISION != "fp32" and B * L > 0 and lib().fs2k_gemm_wgrad_tc_supported(N, K, N, K):
         # tensor cores (tcgen05, MN-major operands); the kernel writes the parameter layout directly
         ws_bytes = lib().fs2k_gemm_wgrad_tc_workspace_bytes(B, L, N, K, taps)
@@ -1073,13 +1095,20 @@ def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0
     return dx, dgamma, dbeta
 
 
-def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None):
+def bn_act_bwd(g, z, scale, shift, mean, rstd, act, training: bool, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None,
+               out_bf16: bool = False):
     g, z = _f32(g, "g"), _f32(z, "z")
     C = z.shape[-1]
     M = z.numel() // C
     sums = torch.empty((2 * C,), dtype=torch.float64, device=z.device)
-    gz = torch.empty_like(z)
     (dgamma, dbeta), acc = _grad_targets(accumulate_into, [(C,), (C,)], z.device)
+    if out_bf16:
+        gz = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device)
+        check(lib().fs2k_bn_act_bwd_bf16(_p(g), _p(z), _p(scale), _p(shift), _p(mean), _p(rstd), _ACTS[act], int(training), M, C,
+                                         float(dropout_p), int(seed), _p(sums), _p(gz), _p(dgamma), _p(dbeta), acc, _stream()), "fs2k_bn_act_bwd_bf16")
+        _count(2)
+        return gz, dgamma, dbeta
+    gz = torch.empty_like(z)
     check(lib().fs2k_bn_act_bwd(_p(g), _p(z), _p(scale), _p(shift), _p(mean), _p(rstd), _ACTS[act], int(training), M, C,
                                 float(dropout_p), int(seed), _p(sums), _p(gz), _p(dgamma), _p(dbeta), acc, _stream()), "fs2k_bn_act_bwd")
     _count(2)

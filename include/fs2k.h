@@ -172,6 +172,19 @@ int fs2k_attention_bf16(const void* qkv_bf16, const int* lens, int B, int L, int
 int fs2k_attention_bwd_bf16(const void* qkv_bf16, const float* out, const float* lse, const float* dout,
                             const void* dout_bf16, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
                             long seed, float* delta, float* dqkv, const int* order, fs2k_stream_t stream);
+/* same with either operand already bf16 in HBM (read by TMA instead of the converting producer warps); ld % 8 == 0 for those */
+int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, const void* X, int x_is_bf16, int ldx, int B, int L,
+                            int N, int K, int taps, int pad, void* workspace, size_t workspace_bytes,
+                            float* dW_param_layout, int accumulate, fs2k_stream_t stream);
+/* fs2k_colsum (bias gradient) of a bf16 matrix */
+int fs2k_colsum_bf16(const void* z_bf16, long M, int C, float* out, int accumulate, fs2k_stream_t stream);
+/* bf16-output variants of fs2k_affine_act / fs2k_bn_act_bwd: the result only feeds tensor-core contractions of the bf16 mode
+ * (its TMA reads bf16 tiles), so it is rounded once where it is produced and the fp32 copy is never written. */
+int fs2k_affine_act_bf16(const float* z, const float* scale, const float* shift, int act, const float* residual, long M,
+                         int C, float dropout_p, long seed, void* y_bf16, fs2k_stream_t stream);
+int fs2k_bn_act_bwd_bf16(const float* g, const float* z, const float* scale, const float* shift, const float* mean,
+                         const float* rstd, int act, int training, long M, int C, float dropout_p, long seed,
+                         double* sums, void* gz_bf16, float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream);
 /* hi[i] = bf16(x[i]); lo[i] = bf16(x[i] - hi[i]) when lo != NULL */
 int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream);
 /* Weight gradient in the bf16 mode (gemm_wgrad_bf16.cu): G, X fp32 in HBM, rounded to bf16 in the kernel, both read as

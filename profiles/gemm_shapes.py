@@ -73,12 +73,14 @@ def wgrad(N, K, taps=1, B=32, L=500):
     return lambda: ops.gemm_wgrad(g, x, taps, (taps - 1) // 2, taps > 1, accumulate_into=acc)
 
 
-def conv(K, N, taps, B=32, L=500):
+def conv(K, N, taps, B=32, L=500, a16=False, hint=None):
     x = torch.randn(B, L, K, device=dev)
     w = torch.randn(taps, N, K, device=dev) / (K * taps) ** 0.5
     if mode == "bf16":
         w16, _ = ops.cast_bf16(w)
-        return lambda: ops.gemm_bf16(x, w16, None, taps_pad=(taps - 1) // 2, block_n_hint=256 if N % 256 == 0 else 0)
+        src = ops.cast_bf16(x)[0] if a16 else x
+        h = hint if hint is not None else (256 if N % 256 == 0 else 0)
+        return lambda: ops.gemm_bf16(src, w16, None, taps_pad=(taps - 1) // 2, block_n_hint=h)
     ops.set_precision(mode)
     return lambda: ops.gemm(x, w, None, taps_pad=(taps - 1) // 2)
 
@@ -100,6 +102,19 @@ bench("encoder linear 256->1024 (M=2560)", lin(256, 1024, silu_pair=True, Mrows=
 bench("encoder linear 1024->256 (M=2560)", lin(1024, 256, residual=True, Mrows=2560), 2.0 * 2560 * 256 * 1024, 2560 * (1024 + 512) * F4)
 bench("postnet conv5 512->512", conv(512, 512, 5), 2.0 * M * 512 * 512 * 5, M * 1024 * F4)
 bench("postnet conv5 80->512", conv(80, 512, 5), 2.0 * M * 80 * 512 * 5, M * 592 * F4)
+if mode == "bf16":
+    bench("postnet conv5 512->512, bf16 A by TMA, BN 256", conv(512, 512, 5, a16=True), 2.0 * M * 512 * 512 * 5, M * (512 * 2 + 512 * 4))
+    bench("postnet conv5 512->512, bf16 A by TMA, BN 128", conv(512, 512, 5, a16=True, hint=-1), 2.0 * M * 512 * 512 * 5, M * (512 * 2 + 512 * 4))
+    xa = ops.cast_bf16(torch.randn(M, 1024, device=dev))[0]
+    wa = ops.cast_bf16(torch.randn(256, 1024, device=dev) / 32)[0]
+    ra = torch.randn(M, 256, device=dev)
+    bench("linear 1024->256 +residual, bf16 A by TMA", lambda: ops.gemm_bf16(xa, wa, None, residual=ra), 2.0 * M * 256 * 1024, M * (1024 * 2 + 512 * 4))
+    xb = torch.randn(M, 256, device=dev)
+    wb = ops.cast_bf16(torch.randn(1024, 256, device=dev) / 16)[0]
+    bench("linear 256->1024 silu, bf16 outputs (pre + value)", lambda: ops.gemm_bf16(xb, wb, None, act="silu", want_c=False, want_c16=True, want_pre="bf16"),
+          2.0 * M * 256 * 1024, M * (256 * 4 + 2048 * 2))
+    bench("linear 256->1024 silu pair, tile-per-CTA kernel", lambda: ops.gemm_bf16(xb, wb, None, act="silu", want_pre="fp32", block_n_hint=-1),
+          2.0 * M * 256 * 1024, M * (256 + 2048) * F4)
 bench("wgrad N=1024 K=256", wgrad(1024, 256), 2.0 * M * 256 * 1024, M * 1280 * F4)
 bench("wgrad N=256 K=1024", wgrad(256, 1024), 2.0 * M * 256 * 1024, M * 1280 * F4)
 bench("wgrad N=256 K=256", wgrad(256, 256), 2.0 * M * 256 * 256, M * 512 * F4)

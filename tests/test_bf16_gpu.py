@@ -225,3 +225,61 @@ def test_gemm_bf16_dropout_mask_matches_the_backward_kernel():
         assert torch.allclose(y[keep], base[keep] / (1 - p), rtol=1e-5, atol=1e-6)
         gz = ops().act_bwd(torch.ones_like(y), None, None, 1.0, None, p, seed)
         assert torch.equal(gz != 0, keep | (base == 0))
+
+
+@pytest.mark.parametrize("g16,x16", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("B,L,N,K,taps", [(3, 300, 512, 512, 5), (2, 200, 512, 80, 5), (2, 200, 80, 512, 5), (3, 500, 1024, 256, 1)])
+def test_gemm_wgrad_bf16_tma_sources(B, L, N, K, taps, g16, x16):
+    g, x = r16(rand(B, L, N, seed=41)), r16(rand(B, L, K, seed=42))
+    pad = (taps - 1) // 2
+    want = ops().gemm_wgrad_bf16(g, x, taps, pad, conv_layout=taps > 1)          # both operands converted in the kernel
+    got = ops().gemm_wgrad_bf16(g.to(torch.bfloat16) if g16 else g, x.to(torch.bfloat16) if x16 else x, taps, pad, conv_layout=taps > 1)
+    assert rel(got, want) <= 1e-6, rel(got, want)   # same bf16 operands, same summation order: identical up to nothing
+
+
+def test_bf16_output_variants_of_the_elementwise_kernels():
+    M, C = 3000, 512
+    z, g = rand(M, C, seed=43), rand(M, C, seed=44)
+    scale, shift = rand(C, seed=45).abs() + 0.5, rand(C, seed=46)
+    mean, rstd = rand(C, seed=47) * 0.1, rand(C, seed=48).abs() + 0.5
+    y = ops().affine_act(z, scale, shift, "tanh", None, 0.3, 11)
+    y16 = ops().affine_act(z, scale, shift, "tanh", None, 0.3, 11, out_bf16=True)
+    assert torch.equal(y16, y.to(torch.bfloat16))
+    gz, dg, db = ops().bn_act_bwd(g, z, scale, shift, mean, rstd, "tanh", True, 0.3, 11)
+    gz16, dg2, db2 = ops().bn_act_bwd(g, z, scale, shift, mean, rstd, "tanh", True, 0.3, 11, out_bf16=True)
+    assert torch.equal(gz16, gz.to(torch.bfloat16)) and torch.equal(dg, dg2) and torch.equal(db, db2)
+    assert rel(ops().colsum(gz16), ops().colsum(gz16.float())) <= 1e-6
+
+
+def test_postnet_bf16_node_follows_the_per_layer_path():
+    """The single-node bf16 PostNet (bf16 activations between the layers, TMA-fed convolutions in all three directions)
+    against the per-layer 3xTF32 path: forward, input gradient and every parameter gradient."""
+    from fastspeech2_lightning_b200 import functional as Fk, ops as o
+    from fastspeech2_lightning_b200.fs2.layers import PostNet
+
+    torch.manual_seed(0)
+    pn = PostNet(n_mel_channels=80).to(dev()).train()
+    pn.dropout_in_training = False
+    x = rand(3, 260, 80, seed=49).requires_grad_(True)
+    w = rand(3, 260, 80, seed=50)
+    res = {}
+    for mode in ("tf32x3", "bf16"):
+        o.set_precision(mode)
+        try:
+            for p in pn.parameters():
+                p.grad = None
+            x.grad = None
+            y = Fk.postnet(x, pn, True)
+            (y * w).sum().backward()
+            res[mode] = (y.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in pn.named_parameters()})
+        finally:
+            o.set_precision("tf32x3")
+    y0, dx0, g0 = res["tf32x3"]
+    y1, dx1, g1 = res["bf16"]
+    assert rel(y1, y0) <= 3e-2, rel(y1, y0)
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm()))
+    assert cos(dx1, dx0) >= 0.995, cos(dx1, dx0)
+    for n in g0:
+        if float(g0[n].norm()) < 1e-4:
+            continue  # conv biases in front of a batch-statistic BatchNorm: analytically zero
+        assert cos(g1[n], g0[n]) >= 0.99, (n, cos(g1[n], g0[n]))
