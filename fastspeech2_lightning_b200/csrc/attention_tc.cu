@@ -111,6 +111,8 @@ attention_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
     at_setup(&bars, &s_tmem, warp, lane, 256);
     const uint32_t tmem = s_tmem, tmem_S = tmem, tmem_O = tmem + 128;
     pdl_wait();
+    lens = pdl_acquire(lens);
+    order = pdl_acquire(order);
 
     const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT;
     const int D = H * AT;
@@ -293,6 +295,10 @@ attention_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     at_setup(&bars, &s_tmem, warp, lane, 512);
     const uint32_t tmem = s_tmem;
     pdl_wait();
+    lens = pdl_acquire(lens);
+    order = pdl_acquire(order);
+    lse = pdl_acquire(lse);
+    delta = pdl_acquire(delta);
 
     const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT;
     const int D = H * AT;
@@ -393,6 +399,10 @@ attention_tc_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     at_setup(&bars, &s_tmem, warp, lane, 512);
     const uint32_t tmem = s_tmem;
     pdl_wait();
+    lens = pdl_acquire(lens);
+    order = pdl_acquire(order);
+    lse = pdl_acquire(lse);
+    delta = pdl_acquire(delta);
 
     const int b = order ? order[blockIdx.z] : blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * AT;
     const int D = H * AT;

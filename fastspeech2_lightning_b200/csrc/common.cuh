@@ -31,6 +31,17 @@ extern int g_fs2k_pdl_enabled;  // lib.cu
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A kernel that does work between launch and pdl_wait() (barrier init, TMEM allocation) must re-acquire, AFTER the wait,
+// every pointer to data an earlier kernel may have produced: loads through `const __restrict__` pointers are ld.global.nc —
+// immutable for the kernel's lifetime as far as the compiler knows — and ptxas hoists them above griddepcontrol.wait to hide
+// their latency (seen in SASS: LDG.E.CONSTANT ahead of ACQBULK).  Under a deep chain of programmatically launched kernels
+// that read happens before the producer has run.  The empty volatile asm makes the pointer value unknown until after the wait.
+// tests/test_cabi.py scans the SASS of every kernel for a global access ahead of ACQBULK.
+template <typename T>
+__device__ __forceinline__ T* pdl_acquire(T* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
 __device__ __forceinline__ void pdl_prologue() {
     pdl_launch_dependents();
     pdl_wait();

@@ -41,3 +41,32 @@ def test_product_path_has_no_cpu_fallback():
         ops.layernorm(torch.zeros(2, 8), torch.ones(8), torch.zeros(8))
     with pytest.raises(_lib.Fs2kError):
         _lib.require_device()
+
+
+def test_no_kernel_touches_global_memory_before_its_programmatic_launch_wait():
+    """Every kernel of the library is launched with programmatic stream serialization: it may start while its predecessors
+    are still running and must not read or write global memory before griddepcontrol.wait (SASS: ACQBULK).  ptxas hoists
+    `const __restrict__` loads (LDG.E.CONSTANT) above the wait when a kernel does set-up work first — that made the tensor-core
+    attention kernels read `order` / `lens` before their producer had run (first CUDA-graph replay only).  Scan the SASS."""
+    import re
+    import shutil
+    import subprocess
+
+    import pytest
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    access = re.compile(r"\b(LDG|LD\.E|STG|ST\.E|ATOMG|REDG|RED\.E|UTMALDG|UTMASTG|UBLKCP)\b")
+    bad, fn, waited, n_fn = [], None, False, 0
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn, waited = line.split("Function :")[1].strip(), False
+            n_fn += 1
+        elif "ACQBULK" in line:
+            waited = True
+        elif fn and not waited and access.search(line):
+            bad.append((fn, line.strip()[:90]))
+            waited = True  # one report per kernel
+    assert n_fn > 100
+    assert not bad, bad
