@@ -261,6 +261,66 @@ def conv1d_bn_act(x, weight, bias, bn, act, training, dropout_p=0.0):
     return _ConvBnAct.apply(x.contiguous(), weight, bias, bn.weight, bn.bias, bn, act, training, float(dropout_p))
 
 
+class _FfnHalfBf16(torch.autograd.Function):
+    """x + ½·Dropout(W2·Dropout(SiLU(W1·LN(x) + b1)) + b2) — one half-step feed-forward module of a Conformer layer
+    (torchaudio conformer.py:91-119,185-187,207-209) in the bf16 mode as ONE autograd node.
+
+    forward : LN → row-panel GEMM whose epilogue writes the pre-activation AND dropout(SiLU(·)) in bf16 (the 1024-wide hidden
+              tensors never exist in fp32) → TMA-fed GEMM with bias, dropout, ½ and the residual in its epilogue.
+    backward: dropout-mask/½ on g → row-panel data-gradient GEMM whose epilogue multiplies by SiLU'(pre)·mask and writes bf16 →
+              TMA-fed data-gradient GEMM → LayerNorm backward with the skip connection's gradient added in the same launch;
+              weight / bias gradients (bf16 operands by TMA) on the side stream."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, p_drop):
+        ln, mean, rstd = ops.layernorm(x, ln_w, ln_b, eps, save_stats=True)
+        seed1, seed2 = _seed(p_drop), _seed(p_drop)
+        w1_16, _ = ops.bf16_weight(w1.detach())
+        w2_16, _ = ops.bf16_weight(w2.detach())
+        _, h16, pre16 = ops.gemm_bf16(ln, w1_16, b1.detach(), act="silu", want_c=False, want_c16=True, want_pre="bf16",
+                                      dropout_p=p_drop, seed=seed1)
+        y, _, _ = ops.gemm_bf16(h16, w2_16, b2.detach(), alpha=0.5, residual=x, dropout_p=p_drop, seed=seed2)
+        ctx.save_for_backward(x, ln, mean, rstd, pre16, h16, w1_16, w2_16)
+        ctx.cfg = (p_drop, seed1, seed2)
+        ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, ln, mean, rstd, pre16, h16, w1_16, w2_16 = ctx.saved_tensors
+        p_drop, seed1, seed2 = ctx.cfg
+        ln_w, ln_b, w1, b1, w2, b2 = ctx.params
+        g = g.contiguous()
+        gz = ops.act_bwd(g, None, None, 0.5, None, p_drop, seed2)                       # ½ and the outer dropout mask
+        _, gz1_16 = ops.gemm_bf16_dact(gz, w2_16, pre16, "silu", w_mn=True, dropout_p=p_drop, seed=seed1)   # (gz·W2)∘SiLU'(pre)∘mask
+        dln, _, _ = ops.gemm_bf16(gz1_16, w1_16.reshape(1, *w1_16.shape), None, w_mn=True)
+        sink = _SINK
+        grads = [None] * 6
+        direct = _direct_grads(w1, b1, w2, b2)
+        if sink is not None and direct is not None:
+            sink.stream.wait_stream(torch.cuda.current_stream())
+            sink.keep.append((gz, gz1_16, h16, ln))
+            with torch.cuda.stream(sink.stream):
+                ops.colsum(gz, out=b2.grad, accumulate=True)
+                ops.gemm_wgrad_bf16(gz, h16, 1, 0, False, accumulate_into=w2.grad)
+                ops.colsum(gz1_16, out=b1.grad, accumulate=True)
+                ops.gemm_wgrad_bf16(gz1_16, ln, 1, 0, False, accumulate_into=w1.grad)
+        else:
+            grads[5], grads[4] = ops.colsum(gz), ops.gemm_wgrad_bf16(gz, h16, 1, 0, False)
+            grads[3], grads[2] = ops.colsum(gz1_16), ops.gemm_wgrad_bf16(gz1_16, ln, 1, 0, False)
+        direct_ln = _direct_grads(ln_w, ln_b)
+        dx, dgamma, dbeta = ops.layernorm_bwd(dln, x, mean, rstd, ln_w, accumulate_into=direct_ln, add=g)
+        if direct_ln is None:
+            grads[0], grads[1] = dgamma, dbeta
+        return dx, grads[0], grads[1], None, grads[2], grads[3], grads[4], grads[5], None
+
+
+def ffn_half_bf16(x, ffn, p_drop):
+    s = ffn.sequential
+    return _FfnHalfBf16.apply(x.contiguous(), s[0].weight, s[0].bias, s[0].eps, s[1].weight, s[1].bias, s[4].weight, s[4].bias, float(p_drop))
+
+
 class _PostNetBf16(torch.autograd.Function):
     """PostNet (fs2/layers.py:143-212: 5 × [Conv1d k5 → BatchNorm1d → tanh (not on the last) → Dropout 0.5]) in the bf16 mode
     as ONE autograd node.  Between the layers the activations exist only in bf16 (written by the BatchNorm-affine + tanh

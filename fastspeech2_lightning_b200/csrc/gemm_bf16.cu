@@ -283,7 +283,8 @@ using namespace fs2k;
 bool fs2k_gemm_bf16_panel_ok(int K, int N, int taps, int a_is_bf16, bool has_lo, bool has_scale);
 int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const void* W, int w_mn, int N, const float* bias, int act,
                                 float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, void* C16,
-                                int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, cudaStream_t s);
+                                int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, const void* dact_pre16,
+                                cudaStream_t s);
 
 extern "C" int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream) {
     FS2K_REQUIRE(n >= 0, FS2K_ERR_BAD_SHAPE);
@@ -310,11 +311,11 @@ extern "C" int fs2k_gemm_bf16_supported(int K, int N, int lda, int taps, int a_i
     return (N % 128) == 0;
 }
 
-extern "C" int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int L, int K, const void* W_hi, const void* W_lo,
-                              int w_mn, int N, int taps, int pad, const float* bias, const float* scale, const float* shift,
-                              int act, float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
-                              void* C16, int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, int block_n_hint,
-                              fs2k_stream_t stream) {
+static int gemm_bf16_impl(const void* A, int a_is_bf16, int lda, int B, int L, int K, const void* W_hi, const void* W_lo,
+                          int w_mn, int N, int taps, int pad, const float* bias, const float* scale, const float* shift,
+                          int act, float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
+                          void* C16, int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, int block_n_hint,
+                          const void* dact_pre16, fs2k_stream_t stream) {
     FS2K_REQUIRE(B >= 0 && L >= 0 && K > 0 && N > 0 && taps >= 1 && pad >= 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE(act >= 0 && act <= 3, FS2K_ERR_UNSUPPORTED);
     FS2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FS2K_ERR_BAD_SHAPE);
@@ -329,9 +330,10 @@ extern "C" int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int 
     FS2K_REQUIRE(nsplit == 1 || !a_is_bf16, FS2K_ERR_UNSUPPORTED);  // the lo part of A comes from its fp32 source
     // the model's dominant class (fp32 activations, K <= 256, one tap): row-panel kernel, gemm_bf16_panel.cu
     // (block_n_hint < 0 forces the tile-per-CTA kernel below — A/B measurements)
-    if (block_n_hint >= 0 && fs2k_gemm_bf16_panel_ok(K, N, taps, a_is_bf16, W_lo != nullptr, scale != nullptr))
+    if ((block_n_hint >= 0 || dact_pre16) && fs2k_gemm_bf16_panel_ok(K, N, taps, a_is_bf16, W_lo != nullptr, scale != nullptr))
         return fs2k_gemm_bf16_panel_launch((const float*)A, lda, M, K, W_hi, w_mn, N, bias, act, alpha, residual, ldr, row_mask, C, ldc,
-                                           C16, ldc16, P32, P16, ldp, dropout_p, seed, (cudaStream_t)stream);
+                                           C16, ldc16, P32, P16, ldp, dropout_p, seed, dact_pre16, (cudaStream_t)stream);
+    FS2K_REQUIRE(!dact_pre16, FS2K_ERR_UNSUPPORTED);  // the fused activation-derivative epilogue lives in the row-panel kernel
     int block_n = N <= 256 ? N : 128;
     if (N > 128 && N % 128 == 0) block_n = 128;            // two CTAs per SM: epilogue of one overlaps the other's main loop
     if (block_n_hint == 256 && N % 256 == 0) block_n = 256;
@@ -423,6 +425,27 @@ extern "C" int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int 
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
+}
+
+extern "C" int fs2k_gemm_bf16(const void* A, int a_is_bf16, int lda, int B, int L, int K, const void* W_hi, const void* W_lo,
+                              int w_mn, int N, int taps, int pad, const float* bias, const float* scale, const float* shift,
+                              int act, float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc,
+                              void* C16, int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, int block_n_hint,
+                              fs2k_stream_t stream) {
+    return gemm_bf16_impl(A, a_is_bf16, lda, B, L, K, W_hi, W_lo, w_mn, N, taps, pad, bias, scale, shift, act, alpha, residual, ldr, row_mask,
+                          C, ldc, C16, ldc16, P32, P16, ldp, dropout_p, seed, block_n_hint, nullptr, stream);
+}
+
+// Data-gradient GEMM fused with the derivative of the activation that followed the forward layer (and its dropout mask):
+//   out[m, n] = (Σ_k G[m, k] · W[k][n]) · act'(pre[m, n]) · keep(seed, m·N + n) / (1 − p)
+// `pre_bf16` [M, N] is the forward GEMM's saved pre-activation (its P16 output).  K <= 256, fp32 G, one tap (row-panel kernel).
+extern "C" int fs2k_gemm_bf16_dact(const float* G, int ldg, long M, int K, const void* W_hi, int w_mn, int N, const void* pre_bf16,
+                                   int act, float alpha, float dropout_p, long seed, float* C, void* C16, fs2k_stream_t stream) {
+    FS2K_REQUIRE(M >= 0 && M < (1L << 31) && K > 0 && N > 0, FS2K_ERR_BAD_SHAPE);
+    FS2K_REQUIRE(pre_bf16 != nullptr, FS2K_ERR_NULL);
+    FS2K_REQUIRE(fs2k_gemm_bf16_panel_ok(K, N, 1, 0, false, false), FS2K_ERR_UNSUPPORTED);
+    return gemm_bf16_impl(G, 0, ldg, 1, (int)M, K, W_hi, nullptr, w_mn, N, 1, 0, nullptr, nullptr, nullptr, act, alpha, nullptr, 0, nullptr,
+                          C, N, C16, N, nullptr, nullptr, N, dropout_p, seed, 0, pre_bf16, stream);
 }
 
 FS2K_DEFINE_SEED_BASE_SETTER(gemm_bf16)

@@ -35,7 +35,21 @@ struct PbEpilogue {
     __nv_bfloat16* C16; int ldc16;
     float* P32; __nv_bfloat16* P16; int ldp;
     float drop_p; unsigned long long seed;
+    const __nv_bfloat16* dact_pre16;   // backward fusion: value *= act'(pre) with pre read here (stride ldp) — then dropout mask
 };
+
+__device__ __forceinline__ float pb_act_grad(float u, int act) {
+    if (act == FS2K_ACT_SILU) {
+        const float sg = 1.0f / (1.0f + expf(-u));
+        return sg * (1.0f + u * (1.0f - sg));
+    }
+    if (act == FS2K_ACT_TANH) {
+        const float t = tanhf(u);
+        return 1.0f - t * t;
+    }
+    if (act == FS2K_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
 
 __device__ __forceinline__ float pb_act(float v, int act) {
     if (act == FS2K_ACT_RELU) return fmaxf(v, 0.f);
@@ -44,7 +58,17 @@ __device__ __forceinline__ float pb_act(float v, int act) {
     return v;
 }
 
-template <bool B_MN, bool DROPOUT>
+// epilogue flavours (template): the store loop is instruction-bound (2 epilogue warps per scheduler), so the generic
+// runtime-`act` path — three compares and an IEEE division per element — is kept out of the common launches
+enum { PB_EPI_PLAIN = 0, PB_EPI_SILU = 1, PB_EPI_GENERIC = 2, PB_EPI_DACT = 3 };
+// SiLU through the SFU: ex2.approx + rcp.approx (≈ 2^-21 relative — two orders below the bf16 rounding of the operands)
+__device__ __forceinline__ float pb_silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float pb_silu_grad_fast(float u) {
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-u));
+    return sg * fmaf(u, 1.0f - sg, 1.0f);
+}
+
+template <bool B_MN, bool DROPOUT, int EPI>
 __global__ void __launch_bounds__(PB_THREADS, 1)
 gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict__ A32, int lda, long M, int K, int N,
                        int tiles_per_cta, PbEpilogue ep) {
@@ -167,6 +191,17 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
         const unsigned long long seed = DROPOUT ? seed_with_base(ep.seed) : 0ull;
         const int act = ep.act;
         const float alpha = ep.alpha;
+        // everything the store loop needs, in registers: base pointers of this lane's first row (rows advance by 2 per step)
+        const long mrow0 = m0 + quad * 32 + rsub;
+        const int rows_left = (int)min((long)32, M - (m0 + quad * 32));   // rows of this warp that exist
+        const float* p_res = ep.residual;
+        const uint8_t* p_mask = ep.row_mask;
+        float* p_C = ep.C;
+        __nv_bfloat16* p_C16 = ep.C16;
+        float* p_P32 = ep.P32;
+        __nv_bfloat16* p_P16 = ep.P16;
+        const __nv_bfloat16* p_pre = ep.dact_pre16;
+        const int ldr = ep.ldr, ldc = ep.ldc, ldc16 = ep.ldc16, ldp = ep.ldp;
         for (int jj = 0; jj < n_tiles; ++jj) {
             const int buf = jj & 1;
             const int ncol = (j_begin + jj) * PB_BN + chalf * 64 + c4 * 4;   // this lane's 4 output columns
@@ -178,16 +213,16 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
             auto load_trip = [&](int rb) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const long m = m0 + quad * 32 + rb + u * 2 + rsub;
+                    const int r = rb + u * 2 + rsub;
                     res_n[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     rm_n[u] = 1.f;
-                    if (m < M) {
-                        if (ep.residual) res_n[u] = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + ncol);
-                        if (ep.row_mask) rm_n[u] = ep.row_mask[m] ? 1.f : 0.f;
+                    if (r < rows_left) {
+                        if (p_res) res_n[u] = *reinterpret_cast<const float4*>(p_res + (size_t)(mrow0 + rb + u * 2) * ldr + ncol);
+                        if (p_mask) rm_n[u] = p_mask[mrow0 + rb + u * 2] ? 1.f : 0.f;
                     }
                 }
             };
-            load_trip(0);
+            if (p_res || p_mask) load_trip(0);
             mbar_wait(smem_u32(&s_tmem_full[buf]), (jj >> 1) & 1);
             tc_fence_after();
             {
@@ -211,27 +246,42 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
                 float4 res[4];
                 float rm[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { res[u] = res_n[u]; rm[u] = rm_n[u]; }
-                if (rb + 8 < 32) load_trip(rb + 8);
+                for (int u = 0; u < 4; ++u) {
+                    res[u] = (p_res || p_mask) ? res_n[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rm[u] = (p_res || p_mask) ? rm_n[u] : 1.f;
+                }
+                if ((p_res || p_mask) && rb + 8 < 32) load_trip(rb + 8);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int r = rb + u * 2 + rsub;
-                    const long m = m0 + quad * 32 + r;
-                    if (m >= M) continue;
+                    if (r >= rows_left) continue;
+                    const size_t m = (size_t)(mrow0 + rb + u * 2);
                     float4 v = *reinterpret_cast<const float4*>(stag + r * PB_STAG_PITCH + c4 * 4);
                     v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-                    if (ep.P32) *reinterpret_cast<float4*>(ep.P32 + (size_t)m * ep.ldp + ncol) = v;
-                    if (ep.P16) *reinterpret_cast<uint2*>(ep.P16 + (size_t)m * ep.ldp + ncol) = hb_pack4(v);
-                    v.x = pb_act(v.x, act) * alpha; v.y = pb_act(v.y, act) * alpha;
-                    v.z = pb_act(v.z, act) * alpha; v.w = pb_act(v.w, act) * alpha;
-                    if (DROPOUT) {
-                        const unsigned long long e = (unsigned long long)m * N + ncol;
-                        drop_apply4(v, seed, e, thr16, inv_keep);
+                    if (p_P32) *reinterpret_cast<float4*>(p_P32 + m * ldp + ncol) = v;
+                    if (p_P16) *reinterpret_cast<uint2*>(p_P16 + m * ldp + ncol) = hb_pack4(v);
+                    if (EPI == PB_EPI_DACT) {  // data-gradient GEMM fused with the activation's derivative (pre-activation saved in bf16)
+                        const uint2 pk = *reinterpret_cast<const uint2*>(p_pre + m * ldp + ncol);
+                        const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+                        const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+                        if (act == FS2K_ACT_SILU) {
+                            v.x *= pb_silu_grad_fast(p0.x); v.y *= pb_silu_grad_fast(p0.y);
+                            v.z *= pb_silu_grad_fast(p1.x); v.w *= pb_silu_grad_fast(p1.y);
+                        } else {
+                            v.x *= pb_act_grad(p0.x, act); v.y *= pb_act_grad(p0.y, act);
+                            v.z *= pb_act_grad(p1.x, act); v.w *= pb_act_grad(p1.y, act);
+                        }
+                    } else if (EPI == PB_EPI_SILU) {
+                        v.x = pb_silu_fast(v.x); v.y = pb_silu_fast(v.y); v.z = pb_silu_fast(v.z); v.w = pb_silu_fast(v.w);
+                    } else if (EPI == PB_EPI_GENERIC) {
+                        v.x = pb_act(v.x, act); v.y = pb_act(v.y, act); v.z = pb_act(v.z, act); v.w = pb_act(v.w, act);
                     }
-                    v.x = (v.x + res[u].x) * rm[u]; v.y = (v.y + res[u].y) * rm[u];
-                    v.z = (v.z + res[u].z) * rm[u]; v.w = (v.w + res[u].w) * rm[u];
-                    if (ep.C) *reinterpret_cast<float4*>(ep.C + (size_t)m * ep.ldc + ncol) = v;
-                    if (ep.C16) *reinterpret_cast<uint2*>(ep.C16 + (size_t)m * ep.ldc16 + ncol) = hb_pack4(v);
+                    if (alpha != 1.0f) { v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha; }
+                    if (DROPOUT) drop_apply4(v, seed, (unsigned long long)m * N + ncol, thr16, inv_keep);
+                    if (p_res) { v.x += res[u].x; v.y += res[u].y; v.z += res[u].z; v.w += res[u].w; }
+                    if (p_mask) { v.x *= rm[u]; v.y *= rm[u]; v.z *= rm[u]; v.w *= rm[u]; }
+                    if (p_C) *reinterpret_cast<float4*>(p_C + m * ldc + ncol) = v;
+                    if (p_C16) *reinterpret_cast<uint2*>(p_C16 + m * ldc16 + ncol) = hb_pack4(v);
                 }
             }
             __syncwarp();  // the staging tile is rewritten by the next accumulator
@@ -256,7 +306,8 @@ bool fs2k_gemm_bf16_panel_ok(int K, int N, int taps, int a_is_bf16, bool has_lo,
 
 int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const void* W, int w_mn, int N, const float* bias, int act,
                                 float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, void* C16,
-                                int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, cudaStream_t s) {
+                                int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, const void* dact_pre16,
+                                cudaStream_t s) {
     EncodeTiledFn encode = get_encode();
     FS2K_REQUIRE(encode != nullptr, FS2K_ERR_ARCH);
     CUtensorMap tmB;
@@ -278,7 +329,7 @@ int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const vo
     const int tiles_per_cta = (n_tiles + groups - 1) / groups;
     groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
     PbEpilogue ep{bias, act, alpha, residual, ldr, row_mask, C, ldc, (__nv_bfloat16*)C16, ldc16, P32, (__nv_bfloat16*)P16, ldp,
-                  dropout_p, (unsigned long long)seed};
+                  dropout_p, (unsigned long long)seed, (const __nv_bfloat16*)dact_pre16};
     const size_t smem = 4 * 16384 + PB_STAGES * 16384 + (size_t)PB_EPI_WARPS * 32 * PB_STAG_PITCH * 4 + 1024;
     dim3 grid(panels, groups);
     cudaError_t e = cudaSuccess;
@@ -288,8 +339,12 @@ int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const vo
         fs2k_launch(kernel, dim3(grid), dim3(PB_THREADS), smem, s, tmB, A, lda, M, K, N, tiles_per_cta, ep);
     };
     const bool drop = dropout_p > 0.f;
-    if (w_mn) { if (drop) launch(gemm_bf16_panel_kernel<true, true>); else launch(gemm_bf16_panel_kernel<true, false>); }
-    else { if (drop) launch(gemm_bf16_panel_kernel<false, true>); else launch(gemm_bf16_panel_kernel<false, false>); }
+    const int epi = dact_pre16 ? PB_EPI_DACT : act == FS2K_ACT_NONE ? PB_EPI_PLAIN : act == FS2K_ACT_SILU ? PB_EPI_SILU : PB_EPI_GENERIC;
+#define PB_CASE(MN, DR, EP) if ((w_mn != 0) == MN && drop == DR && epi == EP) launch(gemm_bf16_panel_kernel<MN, DR, EP>);
+#define PB_CASES(EP) PB_CASE(false, false, EP) PB_CASE(false, true, EP) PB_CASE(true, false, EP) PB_CASE(true, true, EP)
+    PB_CASES(PB_EPI_PLAIN) PB_CASES(PB_EPI_SILU) PB_CASES(PB_EPI_GENERIC) PB_CASES(PB_EPI_DACT)
+#undef PB_CASES
+#undef PB_CASE
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;

@@ -10,8 +10,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, long M, int D, float drop_p,
-                     unsigned long long seed, float* __restrict__ dx, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
+                     unsigned long long seed, const float* __restrict__ g_add, float* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
     pdl_prologue();
     seed = seed_with_base(seed);
     const uint32_t thr16 = drop_thr16(drop_p);
@@ -61,6 +61,10 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                 o.y = rs * (gg[i].y - a - xh[i].y * b);
                 o.z = rs * (gg[i].z - a - xh[i].z * b);
                 o.w = rs * (gg[i].w - a - xh[i].w * b);
+                if (g_add) {  // the residual branch's gradient joins here (x feeds both LN and the skip connection)
+                    const float4 r = reinterpret_cast<const float4*>(g_add + (size_t)m * D)[q];
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
                 reinterpret_cast<float4*>(dx + (size_t)m * D)[q] = o;
             }
         }
@@ -211,9 +215,9 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 
 using namespace fs2k;
 
-extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd,
-                                  const float* gamma, long M, int D, float dropout_p, long seed, float* dx,
-                                  float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream) {
+static int layernorm_bwd_impl(const float* g, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, long M, int D, float dropout_p, long seed, const float* g_add, float* dx,
+                              float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream) {
     const unsigned long long useed = (unsigned long long)seed;
     FS2K_REQUIRE(M >= 0 && D > 0, FS2K_ERR_BAD_SHAPE);
     FS2K_REQUIRE((D & 3) == 0 && D <= 1024, FS2K_ERR_UNSUPPORTED);
@@ -231,11 +235,26 @@ extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* m
     long grid = (M + 31) / 32;
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    if (D <= 256) fs2k_launch(layernorm_bwd_kernel<2>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
-    else if (D <= 512) fs2k_launch(layernorm_bwd_kernel<4>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
-    else fs2k_launch(layernorm_bwd_kernel<8>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, dx, dgamma, dbeta);
+    if (D <= 256) fs2k_launch(layernorm_bwd_kernel<2>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, g_add, dx, dgamma, dbeta);
+    else if (D <= 512) fs2k_launch(layernorm_bwd_kernel<4>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, g_add, dx, dgamma, dbeta);
+    else fs2k_launch(layernorm_bwd_kernel<8>, dim3((int)grid), dim3(256), 0, s, g, x, mean, rstd, gamma, M, D, dropout_p, useed, g_add, dx, dgamma, dbeta);
     FS2K_CHECK_LAUNCH();
     return FS2K_OK;
+}
+
+extern "C" int fs2k_layernorm_bwd(const float* g, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, long M, int D, float dropout_p, long seed, float* dx,
+                                  float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream) {
+    return layernorm_bwd_impl(g, x, mean, rstd, gamma, M, D, dropout_p, seed, nullptr, dx, dgamma, dbeta, accumulate, stream);
+}
+
+// dx = LayerNorm backward + g_add: the gradient of the residual branch (x feeds the LayerNorm AND the skip connection) joins
+// in the same launch instead of in a separate elementwise add
+extern "C" int fs2k_layernorm_bwd_add(const float* g, const float* x, const float* mean, const float* rstd,
+                                      const float* gamma, long M, int D, const float* g_add, float* dx, float* dgamma,
+                                      float* dbeta, int accumulate, fs2k_stream_t stream) {
+    FS2K_REQUIRE(g_add != nullptr || M == 0, FS2K_ERR_NULL);
+    return layernorm_bwd_impl(g, x, mean, rstd, gamma, M, D, 0.f, 0, g_add, dx, dgamma, dbeta, accumulate, stream);
 }
 
 static int bn_act_bwd_impl(const float* g, const float* z, const float* scale, const float* shift,

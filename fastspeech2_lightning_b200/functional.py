@@ -17,10 +17,25 @@ from . import autograd as ag
 # ---------------------------------------------------------------------------------------------
 def _ffn_half(x, ffn, training: bool, p_drop: float):
     """x + ½·FFN(x):  LN → Linear → SiLU → Dropout → Linear → Dropout (conformer.py:103-108,:185-187)."""
+    from . import ops
+
     s = ffn.sequential
+    p = p_drop if training else 0.0
+    D, Hd = s[1].weight.shape[1], s[1].weight.shape[0]
+    if ops.PRECISION == "bf16" and ops.bf16_dact_ok(D, Hd) and Hd % 8 == 0 and D % 16 == 0 and s[1].bias is not None and s[4].bias is not None:
+        if ag._needs_grad(x, *ffn.parameters()) or p > 0.0:
+            from . import autograd_fns as fns
+
+            return fns.ffn_half_bf16(x, ffn, p)
+        # synthesis: the hidden activation only exists in bf16 between the two GEMMs
+        ln = ops.layernorm(x, s[0].weight, s[0].bias, s[0].eps)
+        w1_16, _ = ops.bf16_weight(s[1].weight.detach())
+        w2_16, _ = ops.bf16_weight(s[4].weight.detach())
+        _, h16, _ = ops.gemm_bf16(ln, w1_16, s[1].bias, act="silu", want_c=False, want_c16=True)
+        return ops.gemm_bf16(h16, w2_16, s[4].bias, alpha=0.5, residual=x)[0]
     ln = ag.layernorm(x, s[0].weight, s[0].bias, s[0].eps)
-    h = ag.linear(ln, s[1].weight, s[1].bias, act="silu", dropout=p_drop if training else 0.0)
-    return ag.linear(h, s[4].weight, s[4].bias, alpha=0.5, residual=x, dropout=p_drop if training else 0.0)
+    h = ag.linear(ln, s[1].weight, s[1].bias, act="silu", dropout=p)
+    return ag.linear(h, s[4].weight, s[4].bias, alpha=0.5, residual=x, dropout=p)
 
 
 def conformer_layer(x, lengths, layer, training: bool, order=None):

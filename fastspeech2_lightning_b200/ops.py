@@ -654,6 +654,29 @@ def gemm_bf16(a, w_hi, bias=None, *, w_lo=None, w_mn: bool = False, taps_pad: in
     return c, c16, pre
 
 
+def gemm_bf16_dact(g, w16, pre16, act: str, *, w_mn: bool = True, alpha: float = 1.0, dropout_p: float = 0.0, seed: int = 0,
+                   want_c: bool = False, want_c16: bool = True):
+    """(g · W) ∘ act'(pre16) ∘ dropout mask · alpha — the data-gradient GEMM of a Linear+activation(+dropout) layer fused with the
+    activation's derivative.  g [M,K] fp32 (K ≤ 256), w16 [K,N] bf16 (w_mn) or [N,K], pre16 [M,N] bf16 = the forward's saved
+    pre-activation.  Returns (C fp32 | None, C16 bf16 | None)."""
+    g = _f32(g, "g")
+    K = g.shape[-1]
+    M = g.numel() // K
+    w2 = w16.reshape(w16.shape[-2], w16.shape[-1])
+    N = w2.shape[1] if w_mn else w2.shape[0]
+    assert pre16.dtype == torch.bfloat16 and pre16.is_contiguous() and pre16.numel() == M * N
+    c = torch.empty((*g.shape[:-1], N), dtype=torch.float32, device=g.device) if want_c else None
+    c16 = torch.empty((*g.shape[:-1], N), dtype=torch.bfloat16, device=g.device) if want_c16 else None
+    check(lib().fs2k_gemm_bf16_dact(_p(g), K, M, K, _p(w2), int(w_mn), N, _p(pre16), _ACTS[act], float(alpha), float(dropout_p), int(seed),
+                                    _p(c), _p(c16), _stream()), "fs2k_gemm_bf16_dact")
+    _count()
+    return c, c16
+
+
+def bf16_dact_ok(K: int, N: int) -> bool:
+    return K % 64 == 0 and K <= 256 and N % 128 == 0
+
+
 def _f32_or_bf16(t, name):
     if not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (no CPU path)")
@@ -1084,12 +1107,19 @@ def _grad_targets(into, shapes, device):
     return [torch.empty(s, dtype=torch.float32, device=device) for s in shapes], 0
 
 
-def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None):
+def layernorm_bwd(g, x, mean, rstd, gamma, dropout_p: float = 0.0, seed: int = 0, accumulate_into=None, add=None):
+    """`add`: gradient of the residual branch (same shape as x) summed into dx by the same launch."""
     g, x = _f32(g, "g"), _f32(x, "x")
     D = x.shape[-1]
     M = x.numel() // D
     dx = torch.empty_like(x)
     (dgamma, dbeta), acc = _grad_targets(accumulate_into, [(D,), (D,)], x.device)
+    if add is not None:
+        assert not dropout_p
+        check(lib().fs2k_layernorm_bwd_add(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, _p(_f32(add, "add")), _p(dx), _p(dgamma), _p(dbeta),
+                                           acc, _stream()), "fs2k_layernorm_bwd_add")
+        _count()
+        return dx, dgamma, dbeta
     check(lib().fs2k_layernorm_bwd(_p(g), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), M, D, float(dropout_p), int(seed), _p(dx), _p(dgamma), _p(dbeta), acc, _stream()), "fs2k_layernorm_bwd")
     _count()
     return dx, dgamma, dbeta

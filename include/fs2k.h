@@ -176,6 +176,15 @@ int fs2k_attention_bwd_bf16(const void* qkv_bf16, const float* out, const float*
 int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, const void* X, int x_is_bf16, int ldx, int B, int L,
                             int N, int K, int taps, int pad, void* workspace, size_t workspace_bytes,
                             float* dW_param_layout, int accumulate, fs2k_stream_t stream);
+/* LayerNorm backward with the residual branch's gradient added in the same launch: dx = LN_bwd(g) + g_add */
+int fs2k_layernorm_bwd_add(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma, long M,
+                           int D, const float* g_add, float* dx, float* dgamma, float* dbeta, int accumulate,
+                           fs2k_stream_t stream);
+/* Data-gradient GEMM of the bf16 mode fused with the derivative of the activation (and dropout mask) that followed the forward
+ * layer: out = (G * W) .* act'(pre) .* keep * alpha, pre_bf16 [M,N] = the forward GEMM's saved pre-activation.  fp32 G [M,K],
+ * K <= 256, K % 64 == 0, N % 128 == 0; w_mn as in fs2k_gemm_bf16; C (fp32) and / or C16 (bf16) outputs, row stride N. */
+int fs2k_gemm_bf16_dact(const float* G, int ldg, long M, int K, const void* W_hi, int w_mn, int N, const void* pre_bf16, int act,
+                        float alpha, float dropout_p, long seed, float* C, void* C16, fs2k_stream_t stream);
 /* fs2k_colsum (bias gradient) of a bf16 matrix */
 int fs2k_colsum_bf16(const void* z_bf16, long M, int C, float* out, int accumulate, fs2k_stream_t stream);
 /* bf16-output variants of fs2k_affine_act / fs2k_bn_act_bwd: the result only feeds tensor-core contractions of the bf16 mode

@@ -283,3 +283,57 @@ def test_postnet_bf16_node_follows_the_per_layer_path():
         if float(g0[n].norm()) < 1e-4:
             continue  # conv biases in front of a batch-statistic BatchNorm: analytically zero
         assert cos(g1[n], g0[n]) >= 0.99, (n, cos(g1[n], g0[n]))
+
+
+def test_gemm_bf16_dact_fuses_the_activation_derivative_and_the_dropout_mask():
+    M, K, N, p, seed = 700, 256, 1024, 0.2, 5
+    g, w = rand(M, K, seed=51), rand(K, N, seed=52, scale=K ** -0.5)
+    pre = rand(M, N, seed=53)
+    w16, _ = ops().cast_bf16(w)
+    pre16, _ = ops().cast_bf16(pre)
+    c, c16 = ops().gemm_bf16_dact(g, w16, pre16, "silu", w_mn=True, dropout_p=p, seed=seed, want_c=True)
+    dx, _, _ = ops().gemm_bf16(g, w16.reshape(1, K, N), None, w_mn=True)
+    u = pre16.float().double()
+    sg = torch.sigmoid(u)
+    want = dx.double() * (sg * (1 + u * (1 - sg)))
+    mask = ops().act_bwd(torch.ones(M, N, device=dev()), None, None, 1.0, None, p, seed)   # keep/(1-p) or 0
+    want = (want * mask.double()).float()
+    assert rel(c, want) <= 1e-5, rel(c, want)
+    assert torch.equal(c16, c.to(torch.bfloat16))
+
+
+def test_ffn_half_bf16_node_follows_the_per_op_path():
+    from fastspeech2_lightning_b200 import functional as Fk, ops as o
+    from fastspeech2_lightning_b200.fs2.conformer import _FeedForwardModule
+
+    torch.manual_seed(1)
+    ffn = _FeedForwardModule(256, 1024, dropout=0.0).to(dev())
+    x = rand(3, 170, 256, seed=54).requires_grad_(True)
+    w = rand(3, 170, 256, seed=55)
+    res = {}
+    for mode in ("tf32x3", "bf16"):
+        o.set_precision(mode)
+        try:
+            for p in ffn.parameters():
+                p.grad = None
+            x.grad = None
+            y = Fk._ffn_half(x, ffn, True, 0.0)
+            (y * w).sum().backward()
+            res[mode] = (y.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in ffn.named_parameters()})
+        finally:
+            o.set_precision("tf32x3")
+    (y0, dx0, g0), (y1, dx1, g1) = res["tf32x3"], res["bf16"]
+    assert rel(y1, y0) <= 1e-2, rel(y1, y0)
+    assert rel(dx1, dx0) <= 2e-2, rel(dx1, dx0)
+    for n in g0:
+        assert rel(g1[n], g0[n]) <= 3e-2, (n, rel(g1[n], g0[n]))
+    # with dropout: forward and backward masks agree (the gradient of a zeroed hidden unit is zero): finite-difference-free check
+    o.set_precision("bf16")
+    try:
+        torch.manual_seed(3)
+        x2 = rand(2, 130, 256, seed=56).requires_grad_(True)
+        y = Fk._ffn_half(x2, ffn, True, 0.3)
+        y.sum().backward()
+        assert torch.isfinite(x2.grad).all() and float(x2.grad.abs().mean()) > 0
+    finally:
+        o.set_precision("tf32x3")
