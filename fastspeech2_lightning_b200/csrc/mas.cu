@@ -162,23 +162,25 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
     for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
 }
 
-// T ≤ 1024 (one column per thread): the same recurrence WITHOUT a block barrier per frame.  Row i of warp w needs only the
-// last column of warp w−1 from row i−1, so the warps run as a skewed wavefront: every warp publishes its boundary value
-// into a ring of MAS_RING rows and then its row counter; its right neighbour spins on that counter (shared memory,
-// ≈ 30-cycle polls) instead of the whole CTA meeting at __syncthreads (≈ 370 ns per frame with 32 warps).  A warp may
-// run at most MAS_RING − 1 rows ahead of its right neighbour (ring-slot reuse guard).  Direction words go straight to
-// global memory (one 4-byte store per warp and frame, nothing waits for it).  Arithmetic, tie rule and outputs are
-// those of mas_dp_kernel — bit-exact against the reference.
-constexpr int MAS_RING = 64;
+// T ≤ 1024 (one column per thread): SKEWED BLOCKS of MAS_R frames per barrier.  Within a warp the left neighbour of a cell comes
+// from __shfl_up, so a warp can run MAS_R consecutive frames without any block-level synchronisation; only lane 0 needs a
+// value from another warp (the previous frame's last column of warp w−1).  Warps therefore work one block apart: in step s
+// warp w computes frames [1 + R(s−w), 1 + R(s−w) + R) and finds the R boundary cells it needs in shared memory, written by
+// warp w−1 one or two steps earlier (three rotating buffers).  One __syncthreads per R frames instead of one per frame:
+// the DP is latency bound and the barrier (≈ 370 ns with 32 warps) was ≈ 90 % of a frame.  A barrier-free variant with
+// shared-memory flags between neighbouring warps was measured slower than one barrier per frame (4.9 vs 2.95 ms at
+// 8000 × 1000: the polling lanes saturate the shared-memory pipe).  Arithmetic, tie rule and outputs are those of
+// mas_dp_kernel — bit-exact against the reference.  Direction words go straight to global memory (one 4-byte store per
+// warp and frame, off the dependency chain).
+constexpr int MAS_R = 8;
 
 template <int PF>
 __global__ void __launch_bounds__(1024, 1)
-mas_dp_wave_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
+mas_dp_skew_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
                    int W, uint32_t* __restrict__ dirs, int* __restrict__ path, int* __restrict__ durations) {
     pdl_wait();
     extern __shared__ float ring[];  // [PF][blockDim]
-    __shared__ float bnd[MAS_RING][32];
-    __shared__ int progress[32];     // last row whose boundary value warp w has published
+    __shared__ float bnd[3][32][MAS_R];
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
     const int n_mel = min(out_lens[b], F);
@@ -199,48 +201,49 @@ mas_dp_wave_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
     const bool live = col < n_text;
     float prev = NEG_INF;
     if (col == 0) prev = x[0];  // row 0: log_p[0,0] = x[0,0]; log_p[0,1:] = -inf (alignment.py:53-54)
-    if (lane == 31) bnd[0][warp] = prev;
-    if (lane == 0) progress[warp] = 0;
-    auto issue = [&](int r) {
-        if (r < n_mel && live) cp_async4(ring + (size_t)(r % PF) * blockDim.x + tid, x + (size_t)r * T + col);
+    // frame 0's boundary cell plays "last frame of block −1": where step w's reader of warp w−1 looks for it
+    if (lane == 31) bnd[(warp + 2) % 3][warp][MAS_R - 1] = prev;
+    int next_issue = 1;  // this thread's frames are consumed in order: stream them PF ahead (one commit group per frame)
+    auto issue = [&]() {
+        if (next_issue < n_mel && live) cp_async4(ring + (size_t)(next_issue % PF) * blockDim.x + tid, x + (size_t)next_issue * T + col);
         cp_async_commit();
+        ++next_issue;
     };
-    for (int r = 1; r <= PF; ++r) issue(r);
+    for (int r = 0; r < PF; ++r) issue();
     __syncthreads();
-    volatile int* vprog = progress;
-    volatile float* vbnd = &bnd[0][0];
 
-    for (int i = 1; i < n_mel; ++i) {
-        cp_async_wait<PF - 1>();
-        const float xv = live ? ring[(size_t)(i % PF) * blockDim.x + tid] : 0.f;
-        float left = __shfl_up_sync(0xffffffffu, prev, 1);
-        if (lane == 0) {
-            if (warp == 0) {
-                left = NEG_INF;
-            } else {
-                while (vprog[warp - 1] < i - 1) {}
-                __threadfence_block();
-                left = vbnd[((i - 1) % MAS_RING) * 32 + warp - 1];
+    const int n_blocks = (n_mel - 1 + MAS_R - 1) / MAS_R;  // frames 1 .. n_mel−1
+    for (int s = 0; s < n_blocks + nwarps - 1; ++s) {
+        const int blk = s - warp;
+        if (blk >= 0 && blk < n_blocks) {
+            const int row0 = 1 + blk * MAS_R;
+            float leftv = NEG_INF;  // lane 0: previous frame's last column of warp w−1, per frame of the block
+#pragma unroll
+            for (int k = 0; k < MAS_R; ++k) {
+                const int i = row0 + k;
+                if (i >= n_mel) break;  // warp-uniform
+                cp_async_wait<PF - 1>();
+                const float xv = live ? ring[(size_t)(i % PF) * blockDim.x + tid] : 0.f;
+                float left = __shfl_up_sync(0xffffffffu, prev, 1);
+                if (lane == 0) {
+                    if (warp > 0) leftv = (k == 0) ? bnd[(s + 1) % 3][warp - 1][MAS_R - 1] : bnd[(s + 2) % 3][warp - 1][k - 1];
+                    left = leftv;
+                }
+                const float up = prev;
+                const bool diag = (left >= up) && (col >= 1);  // backtrack predicate of alignment.py:68; column 0 never moves
+                const uint32_t word = __ballot_sync(0xffffffffu, diag && live);
+                if (lane == 0 && warp < W) d[(size_t)i * W + warp] = word;
+                const float m = up > left ? up : left;
+                const float cur = live ? __fadd_rn(xv, m) : NEG_INF;
+                prev = cur;
+                if (lane == 31) bnd[s % 3][warp][k] = cur;
+                issue();
             }
         }
-        const float up = prev;
-        const bool diag = (left >= up) && (col >= 1);  // backtrack predicate of alignment.py:68; column 0 never moves
-        const uint32_t word = __ballot_sync(0xffffffffu, diag && live);
-        if (lane == 0 && warp < W) d[(size_t)i * W + warp] = word;
-        const float m = up > left ? up : left;
-        const float cur = live ? __fadd_rn(xv, m) : NEG_INF;
-        prev = cur;
-        if (lane == 31) {
-            if (warp + 1 < nwarps)
-                while (vprog[warp + 1] < i - MAS_RING + 1) {}  // the slot's previous tenant (row i − RING) has been read
-            vbnd[(i % MAS_RING) * 32 + warp] = cur;
-            __threadfence_block();
-            vprog[warp] = i;
-        }
-        issue(i + PF);
+        __syncthreads();
     }
     cp_async_wait<0>();
-    __syncthreads();  // every warp's direction words are visible to warp 0
+    __syncthreads();
 
     if (warp == 0) {  // backtrack (alignment.py:62-73), 32 frames per step — as in mas_dp_kernel
         int j = n_text - 1;
@@ -322,7 +325,7 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
 }  // namespace fs2k
 
 static int g_mas_wavefront = 1;
-// 1 (default): barrier-free wavefront kernel for T <= 1024; 0: one __syncthreads per frame (A/B measurements, tests)
+// 1 (default): skewed-block kernel for T <= 1024 (one barrier per 8 frames); 0: one __syncthreads per frame (A/B measurements, tests)
 extern "C" int fs2k_mas_set_wavefront(int enabled) {
     g_mas_wavefront = enabled ? 1 : 0;
     return FS2K_OK;
@@ -366,9 +369,9 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
     if (chunks == 1 && g_mas_wavefront) {
         const size_t smem = (size_t)16 * threads * sizeof(float);
         e = cudaSuccess;
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(mas_dp_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(mas_dp_skew_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
-            fs2k_launch_serial(mas_dp_wave_kernel<16>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
+            fs2k_launch_serial(mas_dp_skew_kernel<16>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
             e = cudaGetLastError();
         }
     } else if (chunks == 1) e = launch_mas<1, 16, false>(MAS_ARGS);

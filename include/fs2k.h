@@ -50,8 +50,8 @@ int fs2k_set_pdl(int enabled);
  * attn [B,F,T]: log-probabilities, or probabilities when take_log != 0 (the `torch.log` of :168 fused).
  * out: path [B,F] int32 (text index of every mel frame, -1 on padded frames), durations [B,T] int32
  * (= attn_hard.sum(2), :267-268), hard [B,1,F,T] fp32 0/1 (may be NULL).  T <= 4096. */
-/* T <= 1024 runs a barrier-free wavefront kernel (warps hand their boundary cell to the right neighbour through shared-memory
- * flags instead of meeting at __syncthreads every frame); fs2k_mas_set_wavefront(0) selects the barrier kernel (same results). */
+/* T <= 1024 runs the skewed-block kernel (warps work one block of 8 frames apart, so the block barrier is met once per 8 frames
+ * instead of every frame); fs2k_mas_set_wavefront(0) selects the one-barrier-per-frame kernel (same results). */
 int fs2k_mas_set_wavefront(int enabled);
 size_t fs2k_mas_workspace_bytes(int B, int F, int T);
 int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B, int F, int T,

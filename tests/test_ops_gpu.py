@@ -62,7 +62,7 @@ def test_mas_batched_ragged_matches_reference_b_mas():
 
 @pytest.mark.parametrize("B,F,T,seed", [(32, 500, 80, 0), (4, 1500, 200, 1), (3, 700, 1100, 2), (2, 300, 2500, 3),
                                         (1, 8000, 1000, 4), (5, 33, 32, 5), (2, 64, 1024, 6)])
-@pytest.mark.parametrize("wavefront", [1, 0])  # T <= 1024: barrier-free wavefront kernel (default) / one barrier per frame
+@pytest.mark.parametrize("wavefront", [1, 0])  # T <= 1024: skewed-block kernel, one barrier per 8 frames (default) / one barrier per frame
 def test_mas_random_vs_oracle(B, F, T, seed, wavefront, request):
     from fastspeech2_lightning_b200._lib import lib
 
