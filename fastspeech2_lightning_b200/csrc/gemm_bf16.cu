@@ -276,6 +276,12 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     }
 }
 
+// bf16 → fp32 (the widening side of the bf16 gradient exchange: optim.FusedAdamW.allreduce_range)
+__global__ void __launch_bounds__(256) cast_f32_kernel(const __nv_bfloat16* __restrict__ x, long n, float* __restrict__ y) {
+    pdl_prologue();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = __bfloat162float(x[i]);
+}
+
 }  // namespace fs2k
 
 using namespace fs2k;
@@ -285,6 +291,17 @@ int fs2k_gemm_bf16_panel_launch(const float* A, int lda, long M, int K, const vo
                                 float alpha, const float* residual, int ldr, const uint8_t* row_mask, float* C, int ldc, void* C16,
                                 int ldc16, float* P32, void* P16, int ldp, float dropout_p, long seed, const void* dact_pre16,
                                 cudaStream_t s);
+
+extern "C" int fs2k_cast_f32(const void* x_bf16, long n, float* y, fs2k_stream_t stream) {
+    FS2K_REQUIRE(n >= 0, FS2K_ERR_BAD_SHAPE);
+    if (n == 0) return FS2K_OK;
+    FS2K_REQUIRE(x_bf16 && y, FS2K_ERR_NULL);
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    fs2k_launch(cast_f32_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_bf16, n, y);
+    FS2K_CHECK_LAUNCH();
+    return FS2K_OK;
+}
 
 extern "C" int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream) {
     FS2K_REQUIRE(n >= 0, FS2K_ERR_BAD_SHAPE);

@@ -205,6 +205,11 @@ class FastSpeech2(_Base):
             dec_in = va["output_with_pos"]
         else:
             dec_in = fns.add_posenc(va["output"], inv_freq, ops.mask_lens(tgt_mask))
+        cut = getattr(self, "_backward_cut", None)
+        if cut is not None and torch.is_grad_enabled() and dec_in.requires_grad:
+            # data-parallel training: the backward is run in two phases around this tensor (graphs.GraphedTrainStep), so that the
+            # decoder / PostNet gradients can be all-reduced while the variance adaptor and the encoder are still back-propagating
+            dec_in = cut(dec_in)
         with ops.decoder_precision():  # no discrete decision follows: optional reduced-precision synthesis (ops.set_precision)
             x, _ = self.decoder(dec_in, mel_lens)
             output = ag.linear(x, self.mel_linear.weight, self.mel_linear.bias)

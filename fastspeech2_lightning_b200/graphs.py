@@ -111,7 +111,10 @@ class GraphedTrainStep:
         self._eager_only: set = set()
         self._pool = None
         self.overlap_wgrad = overlap_wgrad
+        self.overlap_allreduce = True   # data-parallel runs: cut the backward at the decoder's input (see _early_params)
         self._sink = None
+        self._early = None
+        self._comm = None
         # every dropout kernel adds *seed_base to its by-value seed (fresh masks on graph replays).  The pointer is
         # process-wide inside the library: it is re-armed before every step of THIS runner (another runner may have
         # pointed it at its own counter) and cleared when the optimizer — the owner of the counter — goes away.
@@ -127,34 +130,101 @@ class GraphedTrainStep:
             check(lib().fs2k_set_dropout_seed_base(ptr), "fs2k_set_dropout_seed_base")
             _ARMED_SEED_BASE = ptr
 
-    def _step_body(self, batch, update: bool = True):
+    def _early_params(self):
+        """Data-parallel runs: the parameters behind the decoder's input (decoder, mel_linear, PostNet).  Their gradients are
+        final when the backward reaches that tensor, so their slice of the flat gradient is all-reduced while the variance
+        adaptor, the aligner and the encoder are still back-propagating.  None when the backward is not cut."""
+        if self._early is None:
+            model, opt = self.model, self.opt
+            early = []
+            if opt.world_size() > 1 and self.overlap_allreduce:
+                mods = [model.decoder, model.mel_linear] + ([model.postnet] if getattr(model, "postnet", None) is not None else [])
+                early = [p for m in mods for p in m.parameters() if p.requires_grad]
+                try:
+                    opt.set_early_bucket(early)
+                except ValueError:
+                    early = []
+            ids = {id(p) for p in early}
+            self._early = (early, [p for p in opt._params if id(p) not in ids])
+        return self._early
+
+    def _forward_backward(self, batch, cut: bool = False):
+        """zero_grad, forward, the seven losses and the backward — all of it, or (cut=True) only down to the decoder's
+        input: then `pending` carries what `_backward_rest` needs.  Returns (detached losses, pending)."""
         from . import autograd_fns as fns
 
         model, opt = self.model, self.opt
         opt.zero_grad()
+        early, _ = self._early_params() if cut else ([], None)
+        holder = {}
+        if early:
+            def _cut(t):
+                holder["up"] = t
+                holder["leaf"] = t.detach().requires_grad_(True)
+                return holder["leaf"]
+            model._backward_cut = _cut
+        prev = None
         if self.overlap_wgrad:
             # second stream: the forward-sum loss (started right after the aligner) and, in the backward, the weight /
             # bias gradients of every contraction, accumulated straight into the flat gradient
             if self._sink is None:
                 self._sink = fns.WgradSink()
             prev = fns.set_wgrad_sink(self._sink)
-            try:
-                out = model(batch)
-                losses = model.loss(out, batch, model.current_epoch)
-                self._sink.fence()  # transposed weights / CTC loss prepared on the side stream during the forward
-                losses["total"].backward()
-            finally:
-                fns.set_wgrad_sink(prev)
-                self._sink.join()
-        else:
+        pending = None
+        try:
             out = model(batch)
             losses = model.loss(out, batch, model.current_epoch)
-            losses["total"].backward()
-        if update:
-            opt.step()
+            if self.overlap_wgrad:
+                self._sink.fence()  # transposed weights / CTC loss prepared on the side stream during the forward
+            if "leaf" in holder:
+                losses["total"].backward(inputs=early + [holder["leaf"]], retain_graph=True)
+                pending = (holder["up"], holder["leaf"], losses["total"])
+            else:
+                losses["total"].backward()
+        finally:
+            model._backward_cut = None
+            if self.overlap_wgrad:
+                fns.set_wgrad_sink(prev)
+                self._sink.join()
         # detached: a loss that kept its autograd graph alive would also keep this step's AccumulateGrad nodes (and
         # their stream) alive into the next capture
-        return {k: v.detach() for k, v in losses.items()}
+        return {k: v.detach() for k, v in losses.items()}, pending
+
+    def _backward_rest(self, pending) -> None:
+        """Second phase of a cut backward: from the decoder's input (with the gradient phase one left on the cut) and from
+        the losses that do not pass through the decoder, into every parameter outside the early bucket."""
+        from . import autograd_fns as fns
+
+        up, leaf, total = pending
+        _, late = self._early_params()
+        prev = fns.set_wgrad_sink(self._sink) if self.overlap_wgrad else None
+        try:
+            torch.autograd.backward([up, total], [leaf.grad, None], inputs=late)
+        finally:
+            if self.overlap_wgrad:
+                fns.set_wgrad_sink(prev)
+                self._sink.join()
+
+    def _exchange(self, first: bool) -> None:
+        """The gradient all-reduce of one bucket, on the communication stream (ordered after what the main stream has been
+        given so far).  first=True: the early bucket; False: everything else."""
+        opt = self.opt
+        lo, hi = opt.early_bucket
+        if self._comm is None:
+            self._comm = torch.cuda.Stream()
+        self._comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            if first:
+                opt.allreduce_range(lo, hi)
+            else:
+                opt.allreduce_range(0, lo)
+                opt.allreduce_range(hi, opt.flat_g.numel())
+
+    def _step_body(self, batch, update: bool = True):
+        losses, _ = self._forward_backward(batch)
+        if update:
+            self.opt.step()
+        return losses
 
     def _key(self, batch):
         t = self.model.config.training
@@ -186,14 +256,26 @@ class GraphedTrainStep:
             prev_validate, va.validate_durations = va.validate_durations, False  # the eager first sight validated
             opt.device_state = True
             torch.cuda.synchronize()
-            # data-parallel: the NCCL all-reduce stays OUTSIDE the graphs (forward/backward graph → eager all-reduce →
-            # update graph); single GPU: one graph for everything
+            # data-parallel: the NCCL all-reduces stay OUTSIDE the graphs.  forward + backward down to the decoder's input
+            # → [all-reduce of the decoder / PostNet gradients ‖ rest of the backward] → all-reduce of the rest → update;
+            # single GPU: one graph for everything
             split = opt.world_size() > 1
+            cut = split and bool(self._early_params()[0])
             graph = torch.cuda.CUDAGraph()
+            graph_rest = torch.cuda.CUDAGraph() if cut else None
             graph2 = torch.cuda.CUDAGraph() if split else None
             try:
                 with torch.cuda.graph(graph, pool=self._pool):
-                    static_losses = self._step_body(static_in, update=not split)
+                    if split:
+                        static_losses, pending = self._forward_backward(static_in, cut=cut)
+                    else:
+                        static_losses = self._step_body(static_in)
+                if cut:
+                    if pending is None:
+                        raise RuntimeError("the forward did not pass the decoder-input cut")
+                    with torch.cuda.graph(graph_rest, pool=graph.pool()):
+                        self._backward_rest(pending)
+                    del pending
                 if split:
                     with torch.cuda.graph(graph2, pool=graph.pool()):
                         opt.step(allreduce=False)
@@ -210,15 +292,21 @@ class GraphedTrainStep:
                 va.validate_durations = prev_validate
             if self._pool is None:
                 self._pool = graph.pool()
-            entry = (graph, static_in, static_losses, graph2)
+            entry = (graph, static_in, static_losses, graph2, graph_rest)
             self._cache[key] = entry
-        graph, static_in, static_losses, graph2 = entry
+        graph, static_in, static_losses, graph2, graph_rest = entry
         for k, v in batch.items():
             if torch.is_tensor(v) and v.dim() > 0 and k in static_in:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         opt.begin_graph_step()
         graph.replay()
-        if graph2 is not None:
+        if graph_rest is not None:
+            self._exchange(first=True)      # decoder / PostNet gradients travel ...
+            graph_rest.replay()             # ... while the variance adaptor, aligner and encoder back-propagate
+            self._exchange(first=False)
+            torch.cuda.current_stream().wait_stream(self._comm)
+            graph2.replay()
+        elif graph2 is not None:
             opt.allreduce_grads()
             graph2.replay()
         if self.sched is not None:

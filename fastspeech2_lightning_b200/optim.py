@@ -44,6 +44,9 @@ class FusedAdamW(torch.optim.Optimizer):
         # so the GEMMs' weight operands need no cast pass; created on first use (ops.bf16_weight)
         self.flat_p16 = None
         self._p16_sig = -1  # Σ parameter version counters at the last sync
+        self.early_bucket = None   # (lo, hi) of the gradients that are final first in the backward (set_early_bucket)
+        self.comm_bf16 = True      # bf16 mode: all-reduce the gradient as bf16
+        self._g16 = None
         with torch.no_grad():
             for p, o in zip(params, offs):
                 view = self.flat_p[o: o + p.numel()].view_as(p)
@@ -86,7 +89,37 @@ class FusedAdamW(torch.optim.Optimizer):
     def allreduce_grads(self) -> None:
         """The data-parallel exchange: one (sum) all-reduce of the flat gradient; the 1/world mean folds into the update."""
         if self.world_size() > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.process_group)
+            self.allreduce_range(0, self.flat_g.numel())
+
+    def set_early_bucket(self, params) -> None:
+        """Mark the parameters whose gradients are final first in the backward (decoder, mel_linear, PostNet): a contiguous
+        slice [lo, hi) of the flat gradient that can be all-reduced while the rest of the backward still runs."""
+        ids = {id(p) for p in params}
+        idx = [i for i, p in enumerate(self._params) if id(p) in ids]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            raise ValueError("the early bucket must be a contiguous run of the optimizer's parameters")
+        lo = self._offs[idx[0]]
+        hi = self._offs[idx[-1] + 1] if idx[-1] + 1 < len(self._offs) else self.flat_g.numel()
+        self.early_bucket = (lo, hi)
+
+    @torch.no_grad()
+    def allreduce_range(self, lo: int, hi: int) -> None:
+        """Sum all-reduce of flat_g[lo:hi] on the current stream.  bf16 arithmetic mode: the gradient travels as bf16 (half the
+        bytes over NVLink; the fp32 master gradient is rounded once on the way out and restored on the way back)."""
+        if hi <= lo or self.world_size() == 1:
+            return
+        g = self.flat_g[lo:hi]
+        if ops.PRECISION == "bf16" and self.comm_bf16:
+            if self._g16 is None:
+                self._g16 = torch.empty(self.flat_g.numel(), dtype=torch.bfloat16, device=self.flat_g.device)
+            g16 = self._g16[lo:hi]
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().fs2k_cast_bf16(g.data_ptr(), g.numel(), g16.data_ptr(), None, stream), "fs2k_cast_bf16")
+            torch.distributed.all_reduce(g16, group=self.process_group)
+            check(lib().fs2k_cast_f32(g16.data_ptr(), g.numel(), g.data_ptr(), stream), "fs2k_cast_f32")
+            ops._count(2)
+        else:
+            torch.distributed.all_reduce(g, group=self.process_group)
 
     @torch.no_grad()
     def step(self, closure=None, allreduce: bool = True):

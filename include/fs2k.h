@@ -196,6 +196,9 @@ int fs2k_bn_act_bwd_bf16(const float* g, const float* z, const float* scale, con
                          double* sums, void* gz_bf16, float* dgamma, float* dbeta, int accumulate, fs2k_stream_t stream);
 /* hi[i] = bf16(x[i]); lo[i] = bf16(x[i] - hi[i]) when lo != NULL */
 int fs2k_cast_bf16(const float* x, long n, void* hi, void* lo, fs2k_stream_t stream);
+/* y = fp32(x): widens a bf16 buffer (gradient exchange in bf16: the reference trains under Lightning DDP, whose
+   `bf16_compress_hook` does the same narrowing around the all-reduce). */
+int fs2k_cast_f32(const void* x_bf16, long n, float* y, fs2k_stream_t stream);
 /* Weight gradient in the bf16 mode (gemm_wgrad_bf16.cu): G, X fp32 in HBM, rounded to bf16 in the kernel, both read as
  * MN-major tcgen05 operands, fp32 accumulation; same outputs as fs2k_gemm_wgrad_tc.  N % 4 == 0, K % 16 == 0,
  * K <= 256 or K % 256 == 0. */

@@ -363,3 +363,43 @@ def test_fused_adamw_adopts_gradients_that_left_the_flat_buffer():
     ref.step()
     close(p, r, 1e-6, "step with a foreign .grad")
     assert p.grad.data_ptr() == opt.flat_g.data_ptr()
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+def test_cut_backward_with_overlapped_exchange_equals_the_single_graph_step(precision, monkeypatch):
+    """Data-parallel step layout on ONE GPU: the backward cut at the decoder's input, the early bucket's all-reduce on the
+    communication stream while the second backward graph runs, then the rest and the update graph.  The all-reduce is
+    replaced by "two ranks with identical gradients" (×2 on the stream it is called on), so the result must equal the
+    plain one-graph step (tests/test_ddp_gpu.py is the same check over real NCCL with two GPUs)."""
+    from fastspeech2_lightning_b200 import ops
+
+    meta, _ = load_case("train_bn")
+    batch = case_batch(meta, DEV)
+    ops.set_precision(precision)
+    try:
+        runs = {}
+        for mode in ("single", "cut"):
+            torch.manual_seed(0)
+            model = _fresh_model(meta)
+            if mode == "cut":
+                calls = []
+
+                def fake_all_reduce(t, group=None, **kw):
+                    calls.append((t.numel(), torch.cuda.current_stream().cuda_stream))
+                    t.mul_(2)
+
+                monkeypatch.setattr(torch.distributed, "all_reduce", fake_all_reduce)
+                monkeypatch.setattr(model.optimizer, "world_size", lambda: 2)
+            traj = [float(model.optimization_step(batch, use_cuda_graph=True)["total"]) for _ in range(4)]
+            runs[mode] = (traj, model.optimizer.flat_p.detach().clone(), model)
+        runner = runs["cut"][2]._train_runner
+        lo, hi = runs["cut"][2].optimizer.early_bucket
+        assert 0 < lo < hi and all(len(e) == 5 and e[4] is not None for e in runner._cache.values())   # the three-graph layout was used
+        main = torch.cuda.current_stream().cuda_stream
+        assert any(n == hi - lo and s != main for n, s in calls), calls       # early bucket went out on the communication stream
+        for a, b in zip(runs["single"][0], runs["cut"][0]):
+            assert abs(a - b) <= (2e-4 if precision == "tf32x3" else 5e-3) * max(1.0, abs(a)), (runs["single"][0], runs["cut"][0])
+        err = float((runs["single"][1] - runs["cut"][1]).abs().max())
+        assert err < (5e-4 if precision == "tf32x3" else 2e-3), err
+    finally:
+        ops.set_precision("tf32x3")
