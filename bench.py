@@ -444,6 +444,13 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
     with ClockSampler(torch.cuda.current_device()) as clk:
         ms_dev = timed(step, args.steps)
         ms_e2e = timed(step_e2e, args.steps)
+    ms_noex = None
+    if world > 1 and graphs and getattr(model, "_train_runner", None) is not None:
+        # the same captured graphs replayed WITHOUT the all-reduces: what the gradient exchange costs per step at this N
+        # (after the timed regions: these steps apply 1/world of the local gradient, so they come last)
+        model._train_runner.skip_exchange = True
+        ms_noex = timed(step, args.steps)
+        model._train_runner.skip_exchange = False
 
     torch.cuda._sleep(int(150e-3 * 1.9e9))
     _lib.start_profile()
@@ -465,10 +472,10 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
                 launches=d[3], algorithmic_bytes_per_launch=d[2] / d[3],
                 shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]})
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_dev, ms_e2e, ms_noex or 0.0], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_noex = float(t[0]), float(t[1]), float(t[2])
     B, T, F = wl["batch"], int(host_batches[0]["max_src_len"]), int(host_batches[0]["max_mel_len"])
     utts = B * args.steps * world
     step_flops = 3 * flops_fwd(B, T, F, aligner=True)
@@ -480,10 +487,12 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         "config": {"workload": workload_string(wl_name, wl, B, T, F),
                    "data_check": "BadDataError check (sum of MAS durations == mel_lens, a host sync per step in the reference) off in the timed steps; the first eager sight of every shape runs it",
                    "l2": "flushed between timed iterations (256 MiB write)", "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}: per-rank replicas, one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "dp1",
+                   "parallelism": (f"dp{world}: per-rank replicas; flat gradient all-reduced over NCCL in two buckets ({'bf16' if ops.PRECISION == 'bf16' else 'fp32'} on the wire), "
+                                   "the decoder/PostNet bucket overlapped with the rest of the backward") if world > 1 else "dp1",
                    "launch": ("cuda graph replay of the whole step (zero_grad, forward, losses, backward, clip, AdamW), one graph per batch shape"
                               if world == 1 else
-                              "two cuda graph replays per step (zero_grad+forward+losses+backward | clip+AdamW) around the eager NCCL all-reduce")
+                              "three cuda graph replays per step (zero_grad+forward+losses+backward to the decoder input | rest of the backward | clip+AdamW); "
+                              "NCCL all-reduces launched between them on a communication stream")
                              if graphs else "eager (one launch per kernel)"},
         "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": batch_bytes(host_batches[0]),
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e / args.steps, "api": "FastSpeech2.optimization_step (training_step + backward + clip + FusedAdamW.step + NoamLR.step)"},
@@ -491,6 +500,10 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         "step_flops": step_flops, "step_tflops": step_flops / (ms_dev / args.steps * 1e-3) / 1e12,
         "gpu_busy_ms_per_step": tot_ms,
     }
+    if world > 1 and ms_noex:
+        line["exchange"] = {"ms_per_step_without_all_reduce": ms_noex / args.steps, "ms_per_step": ms_dev / args.steps,
+                            "exposed_ms": (ms_dev - ms_noex) / args.steps,
+                            "note": "same captured graphs replayed with the NCCL calls skipped, max over ranks: the part of the gradient exchange that is not hidden behind the backward"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = reference_cpu_baseline(wl)
         if line["cpu_baseline"] is None:
@@ -777,7 +790,10 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=device)
+        import datetime
+
+        # a collective that some rank never joins aborts the job after two minutes instead of holding the box until the driver's limit
+        torch.distributed.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=120))
     from fastspeech2_lightning_b200 import ops as _ops
 
     if args.precision is None:

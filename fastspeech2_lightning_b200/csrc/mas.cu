@@ -162,32 +162,43 @@ mas_dp_kernel(const float* __restrict__ attn,   // [B,F,T] log-probs (or probs i
     for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
 }
 
-// T ≤ 1024 (one column per thread): SKEWED BLOCKS of MAS_R frames per barrier.  Within a warp the left neighbour of a cell comes
-// from __shfl_up, so a warp can run MAS_R consecutive frames without any block-level synchronisation; only lane 0 needs a
-// value from another warp (the previous frame's last column of warp w−1).  Warps therefore work one block apart: in step s
-// warp w computes frames [1 + R(s−w), 1 + R(s−w) + R) and finds the R boundary cells it needs in shared memory, written by
-// warp w−1 one or two steps earlier (three rotating buffers).  One __syncthreads per R frames instead of one per frame:
-// the DP is latency bound and the barrier (≈ 370 ns with 32 warps) was ≈ 90 % of a frame.  A barrier-free variant with
-// shared-memory flags between neighbouring warps was measured slower than one barrier per frame (4.9 vs 2.95 ms at
-// 8000 × 1000: the polling lanes saturate the shared-memory pipe).  Arithmetic, tie rule and outputs are those of
-// mas_dp_kernel — bit-exact against the reference.  Direction words go straight to global memory (one 4-byte store per
-// warp and frame, off the dependency chain).
-constexpr int MAS_R = 8;
+// FOUR CONSECUTIVE COLUMNS PER THREAD, SKEWED BLOCKS OF 8 FRAMES (the default kernel).
+// The one-column-per-thread kernel above is issue bound, not latency bound: at T = 1000 its 32 warps share four schedulers and
+// every (warp, frame) costs ≈ 40 instructions for ONE cell per lane — ≈ 350 ns per frame whatever the barrier scheme (measured:
+// one barrier per frame 2.95 ms, one per 8 frames 2.88 ms, shared-memory flags 4.9 ms at 8000 × 1000).  Here a thread owns columns
+// 4t … 4t+3 of the row: one 16-byte shared-memory load and ONE shuffle per four cells (the other three left neighbours are the
+// thread's own registers), ≈ 25 instructions per (thread, frame), and T = 1000 needs 8 warps — two per scheduler.
+//   * Warps run one block of 8 frames apart (warp w works on block s − w in step s): inside a block a warp needs nothing from
+//     the other warps but the previous frames' last column of warp w − 1, which that warp left in shared memory one step earlier
+//     (three rotating buffers, read with two 16-byte loads per block).  One __syncthreads per 8 frames.
+//   * Each thread streams exactly the 16 bytes per frame it will read, PF frames ahead, with cp.async into its own ring slots
+//     (completion per thread: cp.async.wait_group, no barrier); a consumed slot is refilled at once.
+//   * Directions: bit 4k + c of the thread's word for the block = the backtrack predicate of cell (frame 1 + 8·blk + k, column
+//     4t + c); one coalesced 4-byte store per thread and block.  dirs layout: [ceil((F−1)/8)][blockDim] words per utterance.
+//   * Columns ≥ n_text are not masked: a cell only feeds cells to its right, and the backtrack starts at n_text − 1 and moves
+//     left, so whatever they hold is never read.  Arithmetic and tie rule are those of mas_dp_kernel — bit-exact.
+// The backtrack (warp 0, 32 frames per step) gathers, per lane, the 32-column window [j − 31, j] of its frame from ≤ 9 words,
+// then runs the dependent chain on shuffles.
+constexpr int MQ_R = 8;
 
-template <int PF>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int PF, bool VEC>
 __global__ void __launch_bounds__(1024, 1)
-mas_dp_skew_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
-                   int W, uint32_t* __restrict__ dirs, int* __restrict__ path, int* __restrict__ durations) {
+mas_dp_quad_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
+                   uint32_t* __restrict__ dirs, size_t dirs_stride, int* __restrict__ path, int* __restrict__ durations) {
     pdl_wait();
-    extern __shared__ float ring[];  // [PF][blockDim]
-    __shared__ float bnd[3][32][MAS_R];
+    extern __shared__ float4 ring4[];  // [PF][blockDim]
+    __shared__ __align__(16) float bnd[3][32][MQ_R];
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
     const int n_mel = min(out_lens[b], F);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, TQ = blockDim.x;
     const float NEG_INF = -INFINITY;
     const float* x = attn + (size_t)b * F * T;
-    uint32_t* d = dirs + (size_t)b * F * W;
+    uint32_t* d = dirs + (size_t)b * dirs_stride;
     int* p = path + (size_t)b * F;
     int* dur = durations + (size_t)b * T;
 
@@ -197,47 +208,77 @@ mas_dp_skew_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
         for (int f = tid; f < F; f += blockDim.x) p[f] = -1;
         return;
     }
-    const int col = tid;
-    const bool live = col < n_text;
-    float prev = NEG_INF;
-    if (col == 0) prev = x[0];  // row 0: log_p[0,0] = x[0,0]; log_p[0,1:] = -inf (alignment.py:53-54)
-    // frame 0's boundary cell plays "last frame of block −1": where step w's reader of warp w−1 looks for it
-    if (lane == 31) bnd[(warp + 2) % 3][warp][MAS_R - 1] = prev;
-    int next_issue = 1;  // this thread's frames are consumed in order: stream them PF ahead (one commit group per frame)
-    auto issue = [&]() {
-        if (next_issue < n_mel && live) cp_async4(ring + (size_t)(next_issue % PF) * blockDim.x + tid, x + (size_t)next_issue * T + col);
+    const int col0 = 4 * tid;
+    const bool any_live = col0 < n_text;            // this thread copies (and its results can matter)
+    const bool warp_live = warp * 128 < n_text;     // warps right of the text only produce cells nobody reads
+    float p0 = NEG_INF, p1 = NEG_INF, p2 = NEG_INF, p3 = NEG_INF;
+    if (tid == 0) p0 = x[0];  // row 0: log_p[0,0] = x[0,0]; log_p[0,1:] = -inf (alignment.py:53-54)
+    // frame 0's boundary cell plays "last frame of block −1": where warp w + 1 looks for it in its first step
+    if (lane == 31) bnd[(warp + 2) % 3][warp][MQ_R - 1] = p3;
+
+    const int n_steps = n_mel - 1;  // DP frames e = 0 … n_steps − 1 ↔ mel frame e + 1
+    const int n_blocks = (n_steps + MQ_R - 1) / MQ_R;
+    const float* gp = x + (size_t)T + col0;  // this thread's 4 cells of frame 1
+    int e_issue = 0;
+    auto issue = [&](float4* slot) {  // one commit group per frame, also when nothing is copied
+        if (e_issue < n_steps && any_live) {
+            if (VEC) {
+                cp_async16(slot, gp);
+            } else {
+                float* s4 = reinterpret_cast<float*>(slot);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (col0 + c < T) cp_async4(s4 + c, gp + c);
+            }
+        }
         cp_async_commit();
-        ++next_issue;
+        ++e_issue;
+        gp += T;
     };
-    for (int r = 0; r < PF; ++r) issue();
+    for (int r = 0; r < PF; ++r) issue(ring4 + (size_t)r * TQ + tid);
     __syncthreads();
 
-    const int n_blocks = (n_mel - 1 + MAS_R - 1) / MAS_R;  // frames 1 .. n_mel−1
     for (int s = 0; s < n_blocks + nwarps - 1; ++s) {
         const int blk = s - warp;
-        if (blk >= 0 && blk < n_blocks) {
-            const int row0 = 1 + blk * MAS_R;
-            float leftv = NEG_INF;  // lane 0: previous frame's last column of warp w−1, per frame of the block
+        if (blk >= 0 && blk < n_blocks && warp_live) {
+            const int e0 = blk * MQ_R;
+            float bl[MQ_R];  // lane 0's left neighbours: the previous frame's last column of warp w − 1, for each frame of the block
 #pragma unroll
-            for (int k = 0; k < MAS_R; ++k) {
-                const int i = row0 + k;
-                if (i >= n_mel) break;  // warp-uniform
-                cp_async_wait<PF - 1>();
-                const float xv = live ? ring[(size_t)(i % PF) * blockDim.x + tid] : 0.f;
-                float left = __shfl_up_sync(0xffffffffu, prev, 1);
-                if (lane == 0) {
-                    if (warp > 0) leftv = (k == 0) ? bnd[(s + 1) % 3][warp - 1][MAS_R - 1] : bnd[(s + 2) % 3][warp - 1][k - 1];
-                    left = leftv;
+            for (int k = 0; k < MQ_R; ++k) bl[k] = NEG_INF;
+            if (warp > 0) {
+                bl[0] = bnd[(s + 1) % 3][warp - 1][MQ_R - 1];
+                const float4 a = *reinterpret_cast<const float4*>(&bnd[(s + 2) % 3][warp - 1][0]);
+                const float4 c = *reinterpret_cast<const float4*>(&bnd[(s + 2) % 3][warp - 1][4]);
+                bl[1] = a.x; bl[2] = a.y; bl[3] = a.z; bl[4] = a.w; bl[5] = c.x; bl[6] = c.y; bl[7] = c.z;
+            }
+            float bo[MQ_R];
+            uint32_t word = 0;
+            float4* slot = ring4 + (size_t)(e0 % PF) * TQ + tid;  // PF is a multiple of the block: no wrap inside it
+#pragma unroll
+            for (int k = 0; k < MQ_R; ++k) {
+                bo[k] = NEG_INF;
+                if (e0 + k < n_steps) {  // warp-uniform
+                    cp_async_wait<PF - 1>();
+                    const float4 xv = *slot;
+                    float left = __shfl_up_sync(0xffffffffu, p3, 1);
+                    if (lane == 0) left = bl[k];
+                    // backtrack predicate of alignment.py:68 (tie → diagonal); column 0 never moves
+                    const bool d0 = (left >= p0) && (tid != 0), d1 = p0 >= p1, d2 = p1 >= p2, d3 = p2 >= p3;
+                    const float m0 = p0 > left ? p0 : left, m1 = p1 > p0 ? p1 : p0, m2 = p2 > p1 ? p2 : p1, m3 = p3 > p2 ? p3 : p2;
+                    p0 = __fadd_rn(xv.x, m0);  // max(prev_log1, prev_log2) + attn, alignment.py:59
+                    p1 = __fadd_rn(xv.y, m1);
+                    p2 = __fadd_rn(xv.z, m2);
+                    p3 = __fadd_rn(xv.w, m3);
+                    word |= ((d0 ? 1u : 0u) | (d1 ? 2u : 0u) | (d2 ? 4u : 0u) | (d3 ? 8u : 0u)) << (4 * k);
+                    bo[k] = p3;
+                    issue(slot);  // the slot just consumed is refilled PF frames ahead
+                    slot += TQ;
                 }
-                const float up = prev;
-                const bool diag = (left >= up) && (col >= 1);  // backtrack predicate of alignment.py:68; column 0 never moves
-                const uint32_t word = __ballot_sync(0xffffffffu, diag && live);
-                if (lane == 0 && warp < W) d[(size_t)i * W + warp] = word;
-                const float m = up > left ? up : left;
-                const float cur = live ? __fadd_rn(xv, m) : NEG_INF;
-                prev = cur;
-                if (lane == 31) bnd[s % 3][warp][k] = cur;
-                issue();
+            }
+            d[(size_t)blk * TQ + tid] = word;
+            if (lane == 31) {
+                *reinterpret_cast<float4*>(&bnd[s % 3][warp][0]) = make_float4(bo[0], bo[1], bo[2], bo[3]);
+                *reinterpret_cast<float4*>(&bnd[s % 3][warp][4]) = make_float4(bo[4], bo[5], bo[6], bo[7]);
             }
         }
         __syncthreads();
@@ -245,33 +286,39 @@ mas_dp_skew_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
     cp_async_wait<0>();
     __syncthreads();
 
-    if (warp == 0) {  // backtrack (alignment.py:62-73), 32 frames per step — as in mas_dp_kernel
+    if (warp == 0) {  // backtrack (alignment.py:62-73), 32 frames per step
         int j = n_text - 1;
         for (int top = n_mel - 1; top >= 1; top -= 32) {
             const int row = top - lane;
-            const int wj = j >> 5;
-            uint32_t hi = 0, lo = 0;
+            const int jlow = j - 31;
+            uint32_t win = 0;  // bit q ↔ the predicate of cell (row, jlow + q)
             if (row >= 1) {
-                hi = d[(size_t)row * W + wj];
-                if (wj > 0) lo = d[(size_t)row * W + wj - 1];
+                const int e = row - 1, sh = 4 * (e & 7);
+                const uint32_t* dr = d + (size_t)(e >> 3) * TQ;
+                const int tlo = jlow >> 2;  // floor also for negative jlow
+                unsigned long long acc = 0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const int t = tlo + q;
+                    if (t >= 0 && 4 * t <= j) acc |= (unsigned long long)((dr[t] >> sh) & 0xFu) << (4 * t - jlow + 3);
+                }
+                win = (uint32_t)(acc >> 3);
             }
-            const int base = 32 * (wj - 1);
-            int myj = -1;
-#pragma unroll 4
+            int myj = -1, jj = 31;  // jj = j − jlow
+#pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-                if (top - r < 1) break;
-                const uint32_t h = __shfl_sync(0xffffffffu, hi, r);
-                const uint32_t l = __shfl_sync(0xffffffffu, lo, r);
-                if (lane == r) myj = j;
-                const int k = j - base;
-                const uint32_t bit = (k >= 32) ? ((h >> (k - 32)) & 1u) : ((l >> k) & 1u);
-                j -= (int)bit;
+                if (top - r < 1) break;  // warp-uniform
+                const uint32_t h = __shfl_sync(0xffffffffu, win, r);
+                if (lane == r) myj = jlow + jj;
+                jj -= (int)((h >> jj) & 1u);
             }
+            j = jlow + jj;
             if (row >= 1) p[row] = myj;
         }
-        if (lane == 0) p[0] = j;
+        if (lane == 0) p[0] = j;  // opt[0, j] = 1   (alignment.py:73)
     }
     __syncthreads();
+    // durations = attn_hard.sum over frames (variance_adaptor.py:267-268)
     for (int f = tid; f < n_mel; f += blockDim.x) atomicAdd(&dur[p[f]], 1);
 }
 
@@ -325,19 +372,37 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
 }  // namespace fs2k
 
 static int g_mas_wavefront = 1;
-// 1 (default): skewed-block kernel for T <= 1024 (one barrier per 8 frames); 0: one __syncthreads per frame (A/B measurements, tests)
+// 1 (default): four columns per thread, skewed blocks of 8 frames; 0: one column per thread, one __syncthreads per frame
+// (the round-1 kernel, kept for A/B measurements and as a second implementation in the tests)
 extern "C" int fs2k_mas_set_wavefront(int enabled) {
     g_mas_wavefront = enabled ? 1 : 0;
     return FS2K_OK;
 }
 
+static int mas_quad_threads(int T) { return ((T + 3) / 4 + 31) / 32 * 32; }
+static size_t mas_quad_stride(int F, int T) { return (size_t)((F + MQ_R - 1) / MQ_R) * mas_quad_threads(T); }  // words per utterance
 static size_t mas_dirs_bytes(int B, int F, int T) {
-    const size_t n = (size_t)B * F * ((T + 31) / 32) * sizeof(uint32_t);
+    size_t words = (size_t)F * ((T + 31) / 32);
+    if (mas_quad_stride(F, T) > words) words = mas_quad_stride(F, T);
+    const size_t n = (size_t)B * words * sizeof(uint32_t);
     return (n + 255) / 256 * 256;
 }
-// direction words [B,F,ceil(T/32)] + (for take_log) the log-probabilities [B,F,T]
+// direction words + (for take_log) the log-probabilities [B,F,T]
 extern "C" size_t fs2k_mas_workspace_bytes(int B, int F, int T) {
     return mas_dirs_bytes(B, F, T) + (size_t)B * F * T * sizeof(float);
+}
+
+template <int PF, bool VEC>
+static cudaError_t launch_mas_quad(int B, int threads, cudaStream_t s, const float* attn, const int* in_lens, const int* out_lens, int F,
+                                   int T, uint32_t* dirs, int* path, int* durations) {
+    const size_t smem = (size_t)PF * threads * sizeof(float4);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(mas_dp_quad_kernel<PF, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fs2k_launch_serial(mas_dp_quad_kernel<PF, VEC>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, dirs,
+                       mas_quad_stride(F, T), path, durations);
+    return cudaGetLastError();
 }
 
 extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B,
@@ -366,14 +431,15 @@ extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens,
     }
     cudaError_t e;
 #define MAS_ARGS B, threads, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations
-    if (chunks == 1 && g_mas_wavefront) {
-        const size_t smem = (size_t)16 * threads * sizeof(float);
-        e = cudaSuccess;
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(mas_dp_skew_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) {
-            fs2k_launch_serial(mas_dp_skew_kernel<16>, dim3(B), dim3(threads), smem, s, attn, in_lens, out_lens, F, T, W, dirs, path, durations);
-            e = cudaGetLastError();
-        }
+    if (g_mas_wavefront) {
+        const int qt = mas_quad_threads(T);
+        const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(attn) & 15) == 0);
+#define MQ_ARGS B, qt, s, attn, in_lens, out_lens, F, T, dirs, path, durations
+        // ring depth: ≈ 1 µs of frames ahead of the consumer, within the shared memory of one SM
+        if (qt <= 256) e = vec ? launch_mas_quad<32, true>(MQ_ARGS) : launch_mas_quad<32, false>(MQ_ARGS);
+        else if (qt <= 512) e = vec ? launch_mas_quad<16, true>(MQ_ARGS) : launch_mas_quad<16, false>(MQ_ARGS);
+        else e = vec ? launch_mas_quad<8, true>(MQ_ARGS) : launch_mas_quad<8, false>(MQ_ARGS);
+#undef MQ_ARGS
     } else if (chunks == 1) e = launch_mas<1, 16, false>(MAS_ARGS);
     else if (chunks == 2) e = launch_mas<2, 16, false>(MAS_ARGS);
     else { threads = 1024; e = launch_mas<4, 8, false>(MAS_ARGS); }

@@ -86,8 +86,10 @@ extern "C" int fs2k_adamw_step(float* p, const float* g, float* m, float* v, lon
     FS2K_REQUIRE(N >= 0 && step >= 1, FS2K_ERR_BAD_SHAPE);
     if (N == 0) return FS2K_OK;
     FS2K_REQUIRE(p && g && m && v, FS2K_ERR_NULL);
-    const float bc1 = 1.f - powf(beta1, (float)step);
-    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    // double arithmetic on the float betas: the same numbers FusedAdamW.begin_graph_step publishes for a replayed step, so
+    // replicas stay bit-identical when one rank runs this entry point and another replays its captured update
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     long grid = (N + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     fs2k_launch(adamw_kernel, dim3((int)grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, N, lr, beta1, beta2, eps, weight_decay, bc1,

@@ -115,6 +115,7 @@ class GraphedTrainStep:
         self._sink = None
         self._early = None
         self._comm = None
+        self.skip_exchange = False
         # every dropout kernel adds *seed_base to its by-value seed (fresh masks on graph replays).  The pointer is
         # process-wide inside the library: it is re-armed before every step of THIS runner (another runner may have
         # pointed it at its own counter) and cleared when the optimizer — the owner of the counter — goes away.
@@ -220,10 +221,23 @@ class GraphedTrainStep:
                 opt.allreduce_range(0, lo)
                 opt.allreduce_range(hi, opt.flat_g.numel())
 
-    def _step_body(self, batch, update: bool = True):
-        losses, _ = self._forward_backward(batch)
-        if update:
-            self.opt.step()
+    def _step_body(self, batch):
+        """The whole step with eager launches.  Data-parallel runs issue exactly the collectives of the replayed step (same
+        buckets, same order): ranks see their batch shapes in different orders, so one rank may be here — first sight of a
+        shape — while another replays its graphs, and NCCL needs the same sequence of calls on every rank."""
+        opt = self.opt
+        if opt.world_size() > 1 and self._early_params()[0]:
+            losses, pending = self._forward_backward(batch, cut=True)
+            if pending is None:
+                raise RuntimeError("the forward did not pass the decoder-input cut")
+            self._exchange(first=True)
+            self._backward_rest(pending)
+            self._exchange(first=False)
+            torch.cuda.current_stream().wait_stream(self._comm)
+            opt.step(allreduce=False)
+        else:
+            losses, _ = self._forward_backward(batch)
+            opt.step()
         return losses
 
     def _key(self, batch):
@@ -266,10 +280,9 @@ class GraphedTrainStep:
             graph2 = torch.cuda.CUDAGraph() if split else None
             try:
                 with torch.cuda.graph(graph, pool=self._pool):
-                    if split:
-                        static_losses, pending = self._forward_backward(static_in, cut=cut)
-                    else:
-                        static_losses = self._step_body(static_in)
+                    static_losses, pending = self._forward_backward(static_in, cut=cut)
+                    if not split:
+                        opt.step()
                 if cut:
                     if pending is None:
                         raise RuntimeError("the forward did not pass the decoder-input cut")
@@ -300,7 +313,11 @@ class GraphedTrainStep:
                 static_in[k].copy_(v, non_blocking=non_blocking)
         opt.begin_graph_step()
         graph.replay()
-        if graph_rest is not None:
+        if self.skip_exchange and graph2 is not None:   # measurement only (bench.py): the same graphs without the all-reduces
+            if graph_rest is not None:
+                graph_rest.replay()
+            graph2.replay()
+        elif graph_rest is not None:
             self._exchange(first=True)      # decoder / PostNet gradients travel ...
             graph_rest.replay()             # ... while the variance adaptor, aligner and encoder back-propagate
             self._exchange(first=False)

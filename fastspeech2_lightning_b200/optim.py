@@ -8,6 +8,8 @@ hyper-parameters as the reference's `torch.optim.AdamW` (fs2/model.py:530-537) w
 """
 from __future__ import annotations
 
+import math
+import struct
 import weakref
 
 import torch
@@ -247,9 +249,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self._bump_versions()
         self._mark_p16_synced()  # the replayed update kernel writes the bf16 shadow too
         self._opt_called = True  # LRScheduler's "scheduler.step() before optimizer.step()" check
-        b1, b2 = g["betas"]
+        # the betas as the kernels see them (fp32), the corrections in double: exactly what fs2k_adamw_step computes (optimizer.cu)
+        b1, b2 = (struct.unpack("f", struct.pack("f", b))[0] for b in g["betas"])
         seed = int(torch.randint(0, 2**62, (1,)).item())
-        check(lib().fs2k_set_step_state(self.step_state.data_ptr(), self.seed_base.data_ptr(), float(g["lr"]), 1.0 - b1 ** self._step,
-                                        (1.0 - b2 ** self._step) ** 0.5, seed, torch.cuda.current_stream().cuda_stream),
+        check(lib().fs2k_set_step_state(self.step_state.data_ptr(), self.seed_base.data_ptr(), float(g["lr"]), 1.0 - math.pow(b1, self._step),
+                                        math.sqrt(1.0 - math.pow(b2, self._step)), seed, torch.cuda.current_stream().cuda_stream),
               "fs2k_set_step_state")
         ops._count()

@@ -7,6 +7,7 @@ over the padded tensors, loss.py:19-126), BatchNorm uses its running statistics 
 replica — with them the two runs differ by construction) and the epoch-0 weight of the attention binarisation loss is 0
 (it is a ratio of sums, not a mean).
 """
+import datetime
 import os
 import sys
 import tempfile
@@ -58,7 +59,7 @@ def _worker(rank, world, port, precision, ref_path, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    torch.distributed.init_process_group("nccl", device_id=dev)
+    torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     model, halves = _model_and_batches(dev, precision)
     model.configure_optimizers()
     from fastspeech2_lightning_b200 import synthetic
@@ -105,3 +106,45 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(precision,
     print(f"{precision}: 2-rank vs 1-rank parameters after 3 steps: max err / max|p| = {res['err']:.2e}; "
           f"rank-0 losses {res['losses']} vs full-batch {res['ref_losses']}")
     assert res["err"] <= tol, res
+
+
+def _worker_mixed(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+    model, _ = _model_and_batches(dev, "bf16")
+    model.configure_optimizers()
+    from fastspeech2_lightning_b200 import synthetic
+
+    def mk(n, seed):
+        return synthetic.batch_to(synthetic.make_batch(2, (n, n), seed=seed, learn_alignment=True, dur_range=(5, 5), src_lens=[n, n - 5]), dev)
+
+    # rank 0 alternates two shapes (eager, eager, capture, capture, replay, replay); rank 1 repeats one (eager, capture, replay …)
+    seq = [mk(16, 1), mk(12, 2)] * 3 if rank == 0 else [mk(14, 3)] * 6
+    for b in seq:
+        loss = float(model.optimization_step(b)["total"])
+        assert loss == loss
+    flat = model.optimizer.flat_p.detach()
+    both = [torch.empty_like(flat) for _ in range(world)]
+    torch.distributed.all_gather(both, flat)
+    if rank == 0:
+        torch.save({"diff": float((both[0] - both[1]).abs().max()), "cache": len(model._train_runner._cache)}, out_path)
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    os._exit(0)
+
+
+def test_ranks_in_different_step_modes_issue_the_same_collectives():
+    """Ranks meet their batch shapes in different orders, so at the same step one rank may run its eager first sight while the
+    other replays captured graphs: both must issue the same NCCL calls (same buckets, same order) — a mismatch hangs the job
+    (seen at 8 GPUs with one rank drawing the same shape twice).  The replicas stay bit-identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    with tempfile.TemporaryDirectory() as td:
+        out_path = os.path.join(td, "out.pt")
+        mp.spawn(_worker_mixed, args=(2, 29700 + (os.getpid() % 2000), out_path), nprocs=2, join=True)
+        res = torch.load(out_path)
+    assert res["diff"] == 0.0 and res["cache"] == 2, res
