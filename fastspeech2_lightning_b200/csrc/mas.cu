@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(1024, 1)
 mas_dp_quad_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int F, int T,
                    uint32_t* __restrict__ dirs, size_t dirs_stride, int* __restrict__ path, int* __restrict__ durations) {
     pdl_wait();
-    extern __shared__ float4 ring4[];  // [PF][blockDim]
+    extern __shared__ float4 ring4[];  // [PF][blockDim] (a thread-major ring with immediate slot offsets was measured 1.7× slower: the
+                                       // LDGSTS write path wants a warp's 512 bytes contiguous)
     __shared__ __align__(16) float bnd[3][32][MQ_R];
     const int b = blockIdx.x;
     const int n_text = min(in_lens[b], T);
@@ -219,9 +220,9 @@ mas_dp_quad_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
     const int n_steps = n_mel - 1;  // DP frames e = 0 … n_steps − 1 ↔ mel frame e + 1
     const int n_blocks = (n_steps + MQ_R - 1) / MQ_R;
     const float* gp = x + (size_t)T + col0;  // this thread's 4 cells of frame 1
-    int e_issue = 0;
+    int to_issue = any_live ? n_steps : 0;   // frames this thread still has to request
     auto issue = [&](float4* slot) {  // one commit group per frame, also when nothing is copied
-        if (e_issue < n_steps && any_live) {
+        if (to_issue > 0) {
             if (VEC) {
                 cp_async16(slot, gp);
             } else {
@@ -232,12 +233,37 @@ mas_dp_quad_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
             }
         }
         cp_async_commit();
-        ++e_issue;
+        --to_issue;
         gp += T;
     };
-    for (int r = 0; r < PF; ++r) issue(ring4 + (size_t)r * TQ + tid);
+    float4* const my_ring = ring4 + tid;
+    const int rs = TQ;
+    for (int r = 0; r < PF; ++r) issue(my_ring + r * rs);
     __syncthreads();
 
+    uint32_t word = 0;
+    float bo[MQ_R];
+    float4* slot = nullptr;
+    // one frame: max(prev_log1, prev_log2) + attn (alignment.py:59; fmaxf == the reference's max for NaN-free input) and the
+    // backtrack predicate of alignment.py:68 (tie → diagonal; column 0 never moves) for this thread's four cells
+    auto frame = [&](int k, float left_lane0) {
+        cp_async_wait<PF - 1>();
+        const float4 xv = slot[k * rs];
+        float left = __shfl_up_sync(0xffffffffu, p3, 1);
+        if (lane == 0) left = left_lane0;
+        if (left >= p0 && tid != 0) word |= 1u << (4 * k);
+        if (p0 >= p1) word |= 2u << (4 * k);
+        if (p1 >= p2) word |= 4u << (4 * k);
+        if (p2 >= p3) word |= 8u << (4 * k);
+        const float m0 = fmaxf(p0, left), m1 = fmaxf(p1, p0), m2 = fmaxf(p2, p1), m3 = fmaxf(p3, p2);
+        p0 = __fadd_rn(xv.x, m0);
+        p1 = __fadd_rn(xv.y, m1);
+        p2 = __fadd_rn(xv.z, m2);
+        p3 = __fadd_rn(xv.w, m3);
+        bo[k] = p3;
+        issue(slot + k * rs);  // the slot just consumed is refilled PF frames ahead
+    };
+    int b0 = 0, b1 = 1, b2 = 2;  // s % 3, (s + 1) % 3, (s + 2) % 3
     for (int s = 0; s < n_blocks + nwarps - 1; ++s) {
         const int blk = s - warp;
         if (blk >= 0 && blk < n_blocks && warp_live) {
@@ -246,42 +272,32 @@ mas_dp_quad_kernel(const float* __restrict__ attn, const int* __restrict__ in_le
 #pragma unroll
             for (int k = 0; k < MQ_R; ++k) bl[k] = NEG_INF;
             if (warp > 0) {
-                bl[0] = bnd[(s + 1) % 3][warp - 1][MQ_R - 1];
-                const float4 a = *reinterpret_cast<const float4*>(&bnd[(s + 2) % 3][warp - 1][0]);
-                const float4 c = *reinterpret_cast<const float4*>(&bnd[(s + 2) % 3][warp - 1][4]);
+                bl[0] = bnd[b1][warp - 1][MQ_R - 1];
+                const float4 a = *reinterpret_cast<const float4*>(&bnd[b2][warp - 1][0]);
+                const float4 c = *reinterpret_cast<const float4*>(&bnd[b2][warp - 1][4]);
                 bl[1] = a.x; bl[2] = a.y; bl[3] = a.z; bl[4] = a.w; bl[5] = c.x; bl[6] = c.y; bl[7] = c.z;
             }
-            float bo[MQ_R];
-            uint32_t word = 0;
-            float4* slot = ring4 + (size_t)(e0 % PF) * TQ + tid;  // PF is a multiple of the block: no wrap inside it
+            word = 0;
+            slot = my_ring + (e0 % PF) * rs;  // PF is a multiple of the block: no wrap inside it
+            if (e0 + MQ_R <= n_steps) {
 #pragma unroll
-            for (int k = 0; k < MQ_R; ++k) {
-                bo[k] = NEG_INF;
-                if (e0 + k < n_steps) {  // warp-uniform
-                    cp_async_wait<PF - 1>();
-                    const float4 xv = *slot;
-                    float left = __shfl_up_sync(0xffffffffu, p3, 1);
-                    if (lane == 0) left = bl[k];
-                    // backtrack predicate of alignment.py:68 (tie → diagonal); column 0 never moves
-                    const bool d0 = (left >= p0) && (tid != 0), d1 = p0 >= p1, d2 = p1 >= p2, d3 = p2 >= p3;
-                    const float m0 = p0 > left ? p0 : left, m1 = p1 > p0 ? p1 : p0, m2 = p2 > p1 ? p2 : p1, m3 = p3 > p2 ? p3 : p2;
-                    p0 = __fadd_rn(xv.x, m0);  // max(prev_log1, prev_log2) + attn, alignment.py:59
-                    p1 = __fadd_rn(xv.y, m1);
-                    p2 = __fadd_rn(xv.z, m2);
-                    p3 = __fadd_rn(xv.w, m3);
-                    word |= ((d0 ? 1u : 0u) | (d1 ? 2u : 0u) | (d2 ? 4u : 0u) | (d3 ? 8u : 0u)) << (4 * k);
-                    bo[k] = p3;
-                    issue(slot);  // the slot just consumed is refilled PF frames ahead
-                    slot += TQ;
+                for (int k = 0; k < MQ_R; ++k) frame(k, bl[k]);
+            } else {  // the last, partial block
+#pragma unroll
+                for (int k = 0; k < MQ_R; ++k) {
+                    bo[k] = NEG_INF;
+                    if (e0 + k < n_steps) frame(k, bl[k]);
                 }
             }
             d[(size_t)blk * TQ + tid] = word;
             if (lane == 31) {
-                *reinterpret_cast<float4*>(&bnd[s % 3][warp][0]) = make_float4(bo[0], bo[1], bo[2], bo[3]);
-                *reinterpret_cast<float4*>(&bnd[s % 3][warp][4]) = make_float4(bo[4], bo[5], bo[6], bo[7]);
+                *reinterpret_cast<float4*>(&bnd[b0][warp][0]) = make_float4(bo[0], bo[1], bo[2], bo[3]);
+                *reinterpret_cast<float4*>(&bnd[b0][warp][4]) = make_float4(bo[4], bo[5], bo[6], bo[7]);
             }
         }
         __syncthreads();
+        const int t0 = b0;
+        b0 = b1; b1 = b2; b2 = t0;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -371,6 +387,8 @@ static cudaError_t launch_mas(int B, int threads, cudaStream_t s, const float* a
 
 }  // namespace fs2k
 
+using namespace fs2k;
+
 static int g_mas_wavefront = 1;
 // 1 (default): four columns per thread, skewed blocks of 8 frames; 0: one column per thread, one __syncthreads per frame
 // (the round-1 kernel, kept for A/B measurements and as a second implementation in the tests)
@@ -408,7 +426,6 @@ static cudaError_t launch_mas_quad(int B, int threads, cudaStream_t s, const flo
 extern "C" int fs2k_mas_fwd(const float* attn, int take_log, const int* in_lens, const int* out_lens, int B,
                             int F, int T, int* path, int* durations, float* hard, void* workspace,
                             size_t workspace_bytes, fs2k_stream_t stream) {
-    using namespace fs2k;
     FS2K_REQUIRE(B >= 0 && F >= 0 && T >= 0, FS2K_ERR_BAD_SHAPE);
     if (B == 0 || F == 0 || T == 0) return FS2K_OK;
     FS2K_REQUIRE(T <= 4096, FS2K_ERR_UNSUPPORTED);

@@ -24,7 +24,8 @@ def test_strerror_and_argument_validation_without_a_device():
     assert lib.fs2k_mas_fwd(None, 0, None, None, 1, 4, 4, None, None, None, None, 0, None) == -3
     assert lib.fs2k_lr_gather(None, None, None, 1, 4, 6, 8, None, None, None, None, None, None) == -2  # D % 4
     assert lib.fs2k_lr_gather(None, None, None, 1, 4, 8, 8, None, None, None, None, None, None) == -4
-    assert lib.fs2k_mas_workspace_bytes(2, 100, 80) == 2560 + 2 * 100 * 80 * 4  # direction words (256-aligned) + log buffer
+    # direction words (one per thread and block of 8 frames: 13 blocks x 32 threads, 256-aligned) + log buffer
+    assert lib.fs2k_mas_workspace_bytes(2, 100, 80) == 2 * 13 * 32 * 4 + 2 * 100 * 80 * 4
     # empty inputs are a no-op
     assert lib.fs2k_lr_scan(None, 0, 10, None, None, None) == 0
 
