@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1)
 gemm_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                        const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, int L, int N, int K,
                        int tile_k, int taps, int pad, int chunks_per_b, int n_chunks, int chunks_per_split,
-                       float* __restrict__ ws) {
+                       float* __restrict__ ws, float* __restrict__ red_out) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[WB_STAGES], s_empty[WB_STAGES], s_tmem_full;
@@ -145,19 +145,34 @@ gemm_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         tc_fence_after();
         const int q = warp & 3, half = (warp - 4) >> 2;
         const int n = n0 + q * 32 + lane;
-        float* dst = ws + (((size_t)split * taps + tap) * N + n) * K + k0;
-        for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
-            float v[16];
-            if (iters > 0) {
-                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            } else {
+        if (red_out) {
+            // taps == 1: the partial tile is added straight into dW[N][K] with 16-byte reductions resolved in L2 — no workspace
+            // round trip, no reduce launch (profiles/red_probe.cu: 12 µs vs 16–20 µs for the ≈ 19 MB of partial tiles of one launch)
+            float* dst = red_out + (size_t)n * K + k0;
+            if (iters > 0)
+                for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    if (n < N) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            }
-            if (n < N) {
+                        for (int j = 0; j < 16; j += 4) red_add4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+        } else {
+            float* dst = ws + (((size_t)split * taps + tap) * N + n) * K + k0;
+            for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
+                float v[16];
+                if (iters > 0) {
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                if (n < N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
             }
         }
         tc_fence_before();
@@ -236,11 +251,17 @@ extern "C" int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, co
     dim3 grid((N + WB_N - 1) / WB_N, K / tile_k, (unsigned)(splits * taps));
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
+    // taps == 1 and more than one split: partial tiles are reduced in L2 (red.global.add.v4.f32) straight into dW
+    float* red_out = (taps == 1 && splits > 1 && wgrad_atomic_enabled()) ? dW_param_layout : nullptr;
+    if (red_out && !accumulate) {
+        e = cudaMemsetAsync(dW_param_layout, 0, (size_t)N * K * sizeof(float), s);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    }
     auto launch = [&](auto kernel) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return;
         fs2k_launch(kernel, dim3(grid), dim3(WB_THREADS), smem, s, tmG, tmX, g_is_bf16 ? nullptr : (const float*)G, ldg,
-                    x_is_bf16 ? nullptr : (const float*)X, ldx, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+                    x_is_bf16 ? nullptr : (const float*)X, ldx, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace, red_out);
     };
     if (g_is_bf16 && x_is_bf16) launch(gemm_wgrad_bf16_kernel<true, true>);
     else if (g_is_bf16) launch(gemm_wgrad_bf16_kernel<true, false>);
@@ -248,8 +269,10 @@ extern "C" int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, co
     else launch(gemm_wgrad_bf16_kernel<false, false>);
     if (e != cudaSuccess) return fs2k_set_cuda_error(e);
     FS2K_CHECK_LAUNCH();
-    wgrad_reduce_launch((const float*)workspace, splits, taps, N, K, accumulate, dW_param_layout, s);
-    FS2K_CHECK_LAUNCH();
+    if (!red_out) {
+        wgrad_reduce_launch((const float*)workspace, splits, taps, N, K, accumulate, dW_param_layout, s);
+        FS2K_CHECK_LAUNCH();
+    }
     return FS2K_OK;
 }
 

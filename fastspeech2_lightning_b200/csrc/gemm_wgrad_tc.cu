@@ -37,7 +37,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, int L, int N,
                      int K, int tile_k, int taps, int pad, int chunks_per_b, int n_chunks, int chunks_per_split,
-                     float* __restrict__ ws) {
+                     float* __restrict__ ws, float* __restrict__ red_out) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     constexpr int STAGES = WgStages<PASSES>::value;
@@ -128,18 +128,29 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
         tc_fence_after();
         const int q = warp & 3, half = (warp - 4) >> 2;
         const int n = n0 + q * 32 + lane;
-        float* dst = ws + (((size_t)split * taps + tap) * N + n) * K + k0;
-        for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
-            float v[16];
-            if (iters > 0) {
-                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            } else {
+        if (red_out) {  // taps == 1: partial tile added straight into dW[N][K] by 16-byte reductions in L2 (see gemm_wgrad_bf16.cu)
+            float* dst = red_out + (size_t)n * K + k0;
+            if (iters > 0)
+                for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    for (int j = 0; j < 16; j += 4) red_add4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+        } else {
+            float* dst = ws + (((size_t)split * taps + tap) * N + n) * K + k0;
+            for (int c0 = half * 16; c0 < tile_k; c0 += 32) {
+                float v[16];
+                if (iters > 0) {
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         tc_fence_before();
     }
@@ -198,6 +209,15 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int N, i
 }  // namespace fs2k
 
 using namespace fs2k;
+
+static int g_wgrad_atomic = 1;
+// 1 (default): single-tap weight gradients fold their split-K partial tiles into dW with red.global.add.v4.f32 (summation order
+// not fixed: run-to-run differences in the last bits); 0: partial tiles to the workspace + deterministic reduce kernel
+extern "C" int fs2k_wgrad_set_atomic(int enabled) {
+    g_wgrad_atomic = enabled ? 1 : 0;
+    return FS2K_OK;
+}
+bool fs2k::wgrad_atomic_enabled() { return g_wgrad_atomic != 0; }
 
 // shared with gemm_wgrad_bf16.cu (declared in tc_common.cuh)
 int fs2k::wgrad_reduce_launch(const float* ws, int splits, int taps, int N, int K, int accumulate, float* out, cudaStream_t s) {
@@ -265,19 +285,26 @@ extern "C" int fs2k_gemm_wgrad_tc(const float* G, int ldg, const float* X, int l
     dim3 grid(N / WG_N, K / tile_k, (unsigned)(splits * taps));
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
+    float* red_out = (taps == 1 && splits > 1 && wgrad_atomic_enabled()) ? dW_param_layout : nullptr;
+    if (red_out && !accumulate) {
+        e = cudaMemsetAsync(dW_param_layout, 0, (size_t)N * K * sizeof(float), s);
+        if (e != cudaSuccess) return fs2k_set_cuda_error(e);
+    }
     if (passes == 3) {
         e = cudaFuncSetAttribute(gemm_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(gemm_wgrad_tc_kernel<3>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+        fs2k_launch(gemm_wgrad_tc_kernel<3>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace, red_out);
     } else {
         e = cudaFuncSetAttribute(gemm_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fs2k_set_cuda_error(e);
-        fs2k_launch(gemm_wgrad_tc_kernel<1>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace);
+        fs2k_launch(gemm_wgrad_tc_kernel<1>, dim3(grid), dim3(WG_THREADS), smem, s, tmG, tmX, L, N, K, tile_k, taps, pad, chunks_per_b, n_chunks, cps, (float*)workspace, red_out);
     }
     FS2K_CHECK_LAUNCH();
-    const long total4 = ((long)N * K * taps) >> 2;  // N % 128 == 0, so N·K is a multiple of 4
-    fs2k_launch(wgrad_reduce_kernel, dim3((int)((total4 + 31) / 32)), dim3(256), 0, s, (const float*)workspace, splits, taps, N, K, accumulate,
-                                                                 dW_param_layout);
-    FS2K_CHECK_LAUNCH();
+    if (!red_out) {
+        const long total4 = ((long)N * K * taps) >> 2;  // N % 128 == 0, so N·K is a multiple of 4
+        fs2k_launch(wgrad_reduce_kernel, dim3((int)((total4 + 31) / 32)), dim3(256), 0, s, (const float*)workspace, splits, taps, N, K, accumulate,
+                                                                     dW_param_layout);
+        FS2K_CHECK_LAUNCH();
+    }
     return FS2K_OK;
 }

@@ -104,5 +104,10 @@ static EncodeTiledFn get_encode() {
 
 // out (parameter layout) (+)= Σ_split ws[split][tap][n][k] in a fixed order (gemm_wgrad_tc.cu); N·K must be a multiple of 4
 int wgrad_reduce_launch(const float* ws, int splits, int taps, int N, int K, int accumulate, float* out, cudaStream_t s);
+bool wgrad_atomic_enabled();
+// 16-byte floating-point reduction resolved in L2 (sm_90+)
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 }  // namespace fs2k

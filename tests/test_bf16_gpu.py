@@ -337,3 +337,26 @@ def test_ffn_half_bf16_node_follows_the_per_op_path():
         assert torch.isfinite(x2.grad).all() and float(x2.grad.abs().mean()) > 0
     finally:
         o.set_precision("tf32x3")
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+def test_wgrad_l2_reduction_equals_the_workspace_reduce(mode):
+    """Single-tap weight gradients fold their split-K partial tiles into dW with red.global.add.v4.f32 (default) or through the
+    workspace + reduce kernel (fs2k_wgrad_set_atomic(0)): same partial tiles, only the order of the fp32 additions differs."""
+    from fastspeech2_lightning_b200._lib import lib
+
+    g, x = rand(32, 500, 256, seed=51), rand(32, 500, 1024, seed=52)
+    fn = (lambda **kw: ops().gemm_wgrad_bf16(g, x, 1, 0, conv_layout=False, **kw)) if mode == "bf16" else \
+         (lambda **kw: ops().gemm_wgrad(g, x, 1, 0, False, **kw))
+    ops().set_precision(mode)
+    try:
+        got = fn()
+        acc = torch.full_like(got, 2.0)
+        fn(accumulate_into=acc)
+        lib().fs2k_wgrad_set_atomic(0)
+        want = fn()
+    finally:
+        lib().fs2k_wgrad_set_atomic(1)
+        ops().set_precision("tf32x3")
+    assert rel(got, want) <= 2e-6, rel(got, want)
+    assert rel(acc - 2.0, want) <= 1e-5
