@@ -231,7 +231,68 @@ def kernel_work(name, args):
     if name == "fs2k_lr_gather":
         B, T, D, F = args[3], args[4], args[5], args[6]
         return 0.0, 4.0 * B * D * (T + F * (2 if args[8] else 1)) + 4.0 * B * T
+    # memory-bound elementwise / normalisation kernels: bytes each element is read and written once
+    if name == "fs2k_layernorm_fwd":
+        M, D = args[4], args[5]
+        return 0.0, 4.0 * M * (2 * D + 2)
+    if name == "fs2k_layernorm_bwd":
+        M, D = args[5], args[6]
+        return 0.0, 4.0 * M * (3 * D + 2)
+    if name == "fs2k_layernorm_bwd_add":
+        M, D = args[5], args[6]
+        return 0.0, 4.0 * M * (4 * D + 2)
+    if name == "fs2k_dwconv_fwd":
+        B, L, C, glu = args[2], args[3], args[4], args[8]
+        return 0.0, 4.0 * B * L * C * ((2 if glu else 1) + 1)
+    if name == "fs2k_dwconv_bwd":
+        B, L, C, glu = args[3], args[4], args[5], args[8]
+        return 0.0, 4.0 * B * L * C * (1 + 2 * (2 if glu else 1))
+    if name in ("fs2k_colsum", "fs2k_colsum_bf16"):
+        M, C = args[1], args[2]
+        return 0.0, (2.0 if name.endswith("bf16") else 4.0) * M * C
+    if name == "fs2k_act_bwd":
+        M, C = args[5], args[6]
+        return 0.0, 4.0 * M * C * 3
+    if name in ("fs2k_affine_act", "fs2k_affine_act_bf16"):
+        M, C = args[5], args[6]
+        return 0.0, M * C * (4.0 + (4.0 if args[4] else 0.0) + (2.0 if name.endswith("bf16") else 4.0))
+    if name in ("fs2k_bn_act_bwd", "fs2k_bn_act_bwd_bf16"):
+        M, C = args[8], args[9]
+        return 0.0, M * C * (2 * 8.0 + (2.0 if name.endswith("bf16") else 4.0))  # g and z are read by the statistics pass and by the apply pass
+    if name == "fs2k_colstats":
+        return 0.0, 4.0 * args[1] * args[2]
+    if name == "fs2k_aligner_fwd":
+        B, F, T, C = args[4], args[5], args[6], args[7]
+        return 2.0 * B * F * T * C, 4.0 * B * (F * C + T * C + 3 * F * T)
+    if name in ("fs2k_adamw_step", "fs2k_adamw_step_dev"):
+        return 0.0, args[4] * (4.0 * 7 + (2.0 if args[-2] else 0.0))
+    if name == "fs2k_sumsq":
+        return 0.0, 4.0 * args[1]
+    if name in ("fs2k_ctc_forward_sum_fwd", "fs2k_ctc_forward_sum_bwd"):
+        B, F, T = (args[3], args[4], args[5]) if name.endswith("fwd") else (args[7], args[8], args[9])
+        return 0.0, B * F * (4.0 * T + 8.0 * (2 * T + 1)) + (4.0 * B * F * T if name.endswith("bwd") else 0.0)
     return 0.0, 0.0
+
+
+def kernel_table(by, pk, top=24):
+    """Per-entry-point roofline figures of the profiled step: device time, share, achieved TFLOP/s against the measured dense
+    bf16 peak and achieved algorithmic GB/s against the measured HBM peak (whichever the entry point has a formula for),
+    and which of the two ceilings is the lower one for its arithmetic intensity."""
+    tot = sum(d[0] for d in by.values()) or 1.0
+    rows = []
+    for name, d in sorted(by.items(), key=lambda kv: -kv[1][0])[:top]:
+        ms, fl, by_, n = d
+        row = {"entry": name, "launches": n, "ms": round(ms, 4), "share": round(ms / tot, 4)}
+        if fl > 0:
+            row["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
+            row["tensor_frac"] = round(row["tflops"] / pk["tf_sustained"], 4)
+        if by_ > 0:
+            row["gbs"] = round(by_ / (ms * 1e-3) / 1e9, 1)
+            row["hbm_frac"] = round(row["gbs"] / pk["hbm"], 4)
+        if fl > 0 and by_ > 0:
+            row["lower_ceiling"] = "hbm" if by_ / (pk["hbm"] * 1e9) > fl / (pk["tf_sustained"] * 1e12) else "tensor"
+        rows.append(row)
+    return rows
 
 
 def run_ours(args, wl_name, wl, rank, world, device):
@@ -330,7 +391,8 @@ def run_ours(args, wl_name, wl, rank, world, device):
         roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(wl_name, dom), peak_source=pk["source"], share_of_step=d[0] / tot_ms,
                 launches=d[3], algorithmic_bytes_per_launch=d[2] / d[3],
-                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])})
+                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])},
+                by_kernel=kernel_table(by, pk))
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=device)
@@ -470,7 +532,8 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
         roof = {"kernel": dom, "bound": "hbm", "achieved": d[2] / (d[0] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(wl_name, dom), peak_source=pk["source"], share_of_step=d[0] / tot_ms,
                 launches=d[3], algorithmic_bytes_per_launch=d[2] / d[3],
-                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]})
+                shares={k: round(v[0] / tot_ms, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]},
+                by_kernel=kernel_table(by, pk))
 
     t = torch.tensor([ms_dev, ms_e2e, ms_noex or 0.0], dtype=torch.float64, device=device)
     if world > 1:

@@ -193,7 +193,8 @@ static void wgrad_bf16_plan(int B, int L, int N, int K, int taps, int* tile_k, i
     const int chunks_per_b = (L + WB_ROWS - 1) / WB_ROWS;
     const long n_chunks = (long)B * chunks_per_b;
     const long tiles = (long)((N + WB_N - 1) / WB_N) * (K / *tile_k) * taps;
-    long s = (148 + tiles - 1) / tiles;  // one CTA per SM (192 KB of shared memory each)
+    long s = 148 / tiles;  // one CTA per SM (192 KB of shared memory each) and ONE wave: rounding up (152 CTAs for 8 tiles) left a second
+                           // wave of 4 CTAs that doubled the kernel's duration
     if (s > n_chunks) s = n_chunks;
     if (s < 1) s = 1;
     long cps = (n_chunks + s - 1) / s;

@@ -231,7 +231,7 @@ static void wgrad_tc_plan(int B, int L, int N, int K, int taps, int* tile_k, int
     const int chunks_per_b = (L + WG_ROWS - 1) / WG_ROWS;
     const long n_chunks = (long)B * chunks_per_b;
     const long tiles = (long)(N / WG_N) * (K / *tile_k) * taps;
-    long s = (296 + tiles - 1) / tiles;
+    long s = 148 / tiles;  // one CTA per SM (196 KB of shared memory), one wave; a second wave only doubles the partial tiles to reduce
     if (s > n_chunks) s = n_chunks;
     if (s < 1) s = 1;
     long cps = (n_chunks + s - 1) / s;

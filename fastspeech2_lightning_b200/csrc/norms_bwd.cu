@@ -28,20 +28,46 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
         db[i] = dg[i];
     }
     const float inv_d = 1.0f / (float)D;
-    for (long m = (long)blockIdx.x * 8 + warp; m < M; m += (long)gridDim.x * 8) {
-        const float mu = mean[m], rs = rstd[m];
+    // the row loop is a chain of exposed load latencies (load → two warp reductions → store): the next row's operands are
+    // requested before the current row is reduced, so a warp always has two rows of loads in flight
+    const long stride = (long)gridDim.x * 8;
+    float4 gn[MAXV], xn[MAXV];
+    float mun = 0.f, rsn = 0.f;
+    auto fetch = [&](long m) {
+        if (m < M) {
+            mun = mean[m];
+            rsn = rstd[m];
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int q = lane + 32 * i;
+                if (q < D4) {
+                    gn[i] = reinterpret_cast<const float4*>(g + (size_t)m * D)[q];
+                    xn[i] = reinterpret_cast<const float4*>(x + (size_t)m * D)[q];
+                }
+            }
+        }
+    };
+    constexpr bool PIPELINED = MAXV <= 4;  // D = 1024 would spill with two rows of operands in registers
+    if (PIPELINED) fetch((long)blockIdx.x * 8 + warp);
+    for (long m = (long)blockIdx.x * 8 + warp; m < M; m += stride) {
+        if (!PIPELINED) fetch(m);
+        const float mu = mun, rs = rsn;
+        float4 gc[MAXV], xc[MAXV];
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) { gc[i] = gn[i]; xc[i] = xn[i]; }
+        if (PIPELINED) fetch(m + stride);
         float4 gg[MAXV], xh[MAXV];
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int q = lane + 32 * i;
             if (q < D4) {
-                float4 gv = reinterpret_cast<const float4*>(g + (size_t)m * D)[q];
+                float4 gv = gc[i];
                 if (drop_p > 0.f) {  // the forward output was dropout(LN(x)): same mask on the incoming gradient
                     const unsigned long long e = (unsigned long long)m * D + q * 4;
                     drop_apply4(gv, seed, e, thr16, inv_keep);
                 }
-                const float4 xv = reinterpret_cast<const float4*>(x + (size_t)m * D)[q];
+                const float4 xv = xc[i];
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 gg[i] = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
                 a += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
@@ -52,6 +78,14 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
         }
         a = warp_sum(a) * inv_d;
         b = warp_sum(b) * inv_d;
+        float4 radd[MAXV];
+        if (g_add) {  // the residual branch's gradient joins here (x feeds both LN and the skip connection)
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int q = lane + 32 * i;
+                if (q < D4) radd[i] = reinterpret_cast<const float4*>(g_add + (size_t)m * D)[q];
+            }
+        }
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int q = lane + 32 * i;
@@ -61,10 +95,7 @@ layernorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
                 o.y = rs * (gg[i].y - a - xh[i].y * b);
                 o.z = rs * (gg[i].z - a - xh[i].z * b);
                 o.w = rs * (gg[i].w - a - xh[i].w * b);
-                if (g_add) {  // the residual branch's gradient joins here (x feeds both LN and the skip connection)
-                    const float4 r = reinterpret_cast<const float4*>(g_add + (size_t)m * D)[q];
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
+                if (g_add) { o.x += radd[i].x; o.y += radd[i].y; o.z += radd[i].z; o.w += radd[i].w; }
                 reinterpret_cast<float4*>(dx + (size_t)m * D)[q] = o;
             }
         }
