@@ -80,7 +80,7 @@ def ncu_traffic(workload: str, entry_point: str):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel behind `entry_point`, from the
     committed ncu pass of the same workload (profiles/r1_summary_<workload>_v4.json, made by profiles/summarize_launches.py
     from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`); None when there is none."""
-    names = {"fs2k_gemm_tc": ("gemm_tc_kernel",), "fs2k_mas_fwd": ("mas_dp_wave_kernel", "mas_dp_kernel"), "fs2k_attention_f32": ("attention_simt_kernel",),
+    names = {"fs2k_gemm_tc": ("gemm_tc_kernel",), "fs2k_mas_fwd": ("mas_dp_quad_kernel", "mas_dp_kernel"), "fs2k_attention_f32": ("attention_simt_kernel",),
              "fs2k_gemm_bf16": ("gemm_bf16_panel_kernel", "gemm_bf16_kernel"), "fs2k_attention_bf16": ("attention_tc_fwd_kernel",)}
     if entry_point not in names:
         return None
