@@ -30,6 +30,16 @@ def layernorm(x, weight, bias, eps: float = 1e-5, dropout: float = 0.0):
     return ops.layernorm(x, weight, bias, eps)
 
 
+def layernorm_fork(x, weight, bias, eps: float = 1e-5):
+    """(LayerNorm(x), skip) for a pre-norm residual block: use `skip` (== x) as the block's residual input, so that the
+    two gradients of x meet in one backward launch (autograd_fns._LayerNormFork)."""
+    if _needs_grad(x, weight, bias):
+        from . import autograd_fns as fns
+
+        return fns.layernorm_fork(x, weight, bias, eps)
+    return ops.layernorm(x, weight, bias, eps), x
+
+
 def linear(x, weight, bias=None, act=None, alpha: float = 1.0, residual=None, dropout: float = 0.0):
     """act(x·Wᵀ + b)·alpha (+ residual); weight [N,K]."""
     if _needs_grad(x, weight, bias, residual) or dropout > 0.0:

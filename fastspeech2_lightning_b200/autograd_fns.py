@@ -73,6 +73,36 @@ def layernorm(x, weight, bias, eps, dropout_p=0.0):
     return _LayerNorm.apply(x.contiguous(), weight, bias, eps, float(dropout_p))
 
 
+class _LayerNormFork(torch.autograd.Function):
+    """x → (LayerNorm(x), x): the pre-norm residual block `x + f(LayerNorm(x))` takes its skip connection from the second
+    output, so both gradients of x arrive at ONE node and the backward adds them inside the LayerNorm-backward launch
+    (`fs2k_layernorm_bwd_add`) instead of in a separate elementwise add per residual block."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.params = (weight, bias)
+        return y, x.view_as(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, g_skip):
+        x, weight, mean, rstd = ctx.saved_tensors
+        direct = _direct_grads(*ctx.params)
+        if g is None:  # only the skip path was used
+            return g_skip, None, None, None
+        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, weight, accumulate_into=direct,
+                                       add=None if g_skip is None else g_skip.contiguous())
+        if direct is not None:
+            dw = db = None
+        return dx, dw, db, None
+
+
+def layernorm_fork(x, weight, bias, eps):
+    return _LayerNormFork.apply(x.contiguous(), weight, bias, eps)
+
+
 # ---------------------------------------------------------------------------------------------
 class WgradSink:
     """Weight/bias gradients off the critical path.  The data-gradient chain (dgrad GEMM → LayerNorm backward → …) is

@@ -33,27 +33,27 @@ def _ffn_half(x, ffn, training: bool, p_drop: float):
         w2_16, _ = ops.bf16_weight(s[4].weight.detach())
         _, h16, _ = ops.gemm_bf16(ln, w1_16, s[1].bias, act="silu", want_c=False, want_c16=True)
         return ops.gemm_bf16(h16, w2_16, s[4].bias, alpha=0.5, residual=x)[0]
-    ln = ag.layernorm(x, s[0].weight, s[0].bias, s[0].eps)
+    ln, skip = ag.layernorm_fork(x, s[0].weight, s[0].bias, s[0].eps)
     h = ag.linear(ln, s[1].weight, s[1].bias, act="silu", dropout=p)
-    return ag.linear(h, s[4].weight, s[4].bias, alpha=0.5, residual=x, dropout=p)
+    return ag.linear(h, s[4].weight, s[4].bias, alpha=0.5, residual=skip, dropout=p)
 
 
 def conformer_layer(x, lengths, layer, training: bool, order=None):
     p = layer.dropout_p
     x = _ffn_half(x, layer.ffn1, training, p)
     # self-attention block (:191-203)
-    ln = ag.layernorm(x, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, layer.self_attn_layer_norm.eps)
+    ln, skip = ag.layernorm_fork(x, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, layer.self_attn_layer_norm.eps)
     mha = layer.self_attn
     o = ag.qkv_attention(ln, mha.in_proj_weight, mha.in_proj_bias, lengths, layer.num_heads,
                          dropout=mha.dropout if training else 0.0, order=order)
-    x = ag.linear(o, mha.out_proj.weight, mha.out_proj.bias, residual=x, dropout=p if training else 0.0)
+    x = ag.linear(o, mha.out_proj.weight, mha.out_proj.bias, residual=skip, dropout=p if training else 0.0)
     # convolution module (:42-75, :168-174)
     cm = layer.conv_module
     seq = cm.sequential
-    ln = ag.layernorm(x, cm.layer_norm.weight, cm.layer_norm.bias, cm.layer_norm.eps)
+    ln, skip = ag.layernorm_fork(x, cm.layer_norm.weight, cm.layer_norm.bias, cm.layer_norm.eps)
     h = ag.linear(ln, seq[0].weight.squeeze(-1), seq[0].bias)  # pointwise D → 2D (pre-GLU)
     d = ag.glu_dwconv_bn_silu(h, seq[2].weight, seq[2].bias, seq[3], training)
-    x = ag.linear(d, seq[5].weight.squeeze(-1), seq[5].bias, residual=x, dropout=p if training else 0.0)
+    x = ag.linear(d, seq[5].weight.squeeze(-1), seq[5].bias, residual=skip, dropout=p if training else 0.0)
     x = _ffn_half(x, layer.ffn2, training, p)
     fl = layer.final_layer_norm
     return ag.layernorm(x, fl.weight, fl.bias, fl.eps)

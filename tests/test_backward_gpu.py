@@ -52,6 +52,27 @@ def test_layernorm_backward():
     check_grads([fns().layernorm(l[0], l[1], l[2], 1e-5)], [F.layer_norm(r[0], (256,), r[1], r[2], 1e-5)], l, r, what="layernorm")
 
 
+def test_layernorm_fork_adds_the_skip_gradient_in_the_same_launch():
+    """Pre-norm residual block y = x + Linear(LayerNorm(x)): with `layernorm_fork` the skip connection is the node's second
+    output, so dL/dx = LN-backward(g_branch) + g_skip comes out of ONE launch (fs2k_layernorm_bwd_add) — same numbers as
+    the separate LayerNorm node + autograd's accumulation add, one launch fewer."""
+    g = torch.Generator().manual_seed(5)
+    x, w, b = torch.randn(3, 70, 256, generator=g), torch.randn(256, generator=g), torch.randn(256, generator=g)
+    lw, lb = torch.randn(256, 256, generator=g) / 16, torch.randn(256, generator=g)
+    r = [t.clone().requires_grad_(True) for t in (x, w, b, lw, lb)]
+    l = [leaf(t) for t in (x, w, b, lw, lb)]
+    ref = r[0] + F.linear(F.layer_norm(r[0], (256,), r[1], r[2], 1e-5), r[3], r[4])
+    ln, skip = fns().layernorm_fork(l[0], l[1], l[2], 1e-5)
+    assert skip.data_ptr() == l[0].data_ptr()          # no copy of the residual stream
+    out = fns().linear(ln, l[3], l[4], None, 1.0, skip)
+    check_grads([out], [ref], l, r, tol=2e-4, what="layernorm fork")
+    # the skip output alone, and the norm output alone, still back-propagate
+    l2 = leaf(x)
+    _, s2 = fns().layernorm_fork(l2, l[1].detach().requires_grad_(True), l[2].detach().requires_grad_(True), 1e-5)
+    (s2 * 2.0).sum().backward()
+    assert torch.equal(l2.grad, torch.full_like(l2, 2.0))
+
+
 @pytest.mark.parametrize("B,L,K,N,taps,act,res", [(2, 70, 256, 1024, 1, "silu", False), (3, 50, 1024, 256, 1, None, True),
                                                   (2, 90, 80, 512, 5, None, False), (2, 40, 256, 512, 3, "relu", False),
                                                   (2, 33, 512, 80, 5, None, False), (1, 200, 256, 768, 1, None, False)])
