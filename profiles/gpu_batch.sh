@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU call, many answers: every step has its own timeout and log under gpurun_out/, a failing step does not stop the rest.
-# usage (under gpurun): bash profiles/gpu_batch.sh [steps...]   steps: att gemmtests shapes bf16model suite bench_bf16 bench_fp32 bench_x3 synth launches
+# usage (under gpurun): bash profiles/gpu_batch.sh [steps...]   steps: att gemmtests shapes bf16model suite bench_bf16 bench_fp32 bench_x3 synth launches launches_fp32 launches_synth
 mkdir -p gpurun_out
 steps="$@"
 [ -z "$steps" ] && steps="att gemmtests shapes bf16model suite bench_bf16"
@@ -26,6 +26,8 @@ except Exception as e:
 PY
                 done ;;
     launches)   python profiles/one_step.py bf16 train_c2 > gpurun_out/one_step_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_train_bf16.csv python profiles/one_step.py bf16 train_c2 > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log ;;
+    launches_fp32) python profiles/one_step.py tf32x3 train_c2 > gpurun_out/one_step_plain_fp32.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_train_fp32.csv python profiles/one_step.py tf32x3 train_c2 > gpurun_out/ncu_fp32.log 2>&1; tail -2 gpurun_out/ncu_fp32.log ;;
+    launches_synth) python profiles/one_step.py bf16 synth_c1 > gpurun_out/one_step_plain_synth.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_synth_bf16.csv python profiles/one_step.py bf16 synth_c1 > gpurun_out/ncu_synth.log 2>&1; tail -2 gpurun_out/ncu_synth.log ;;
     *) echo "unknown step $s" ;;
   esac
 done
