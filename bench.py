@@ -663,7 +663,7 @@ def run_mas(args, wl_name, wl, rank, world, device, pk):
             "config": {"workload": f"{wl_name}: batched MAS (log + DP + backtrack + dense map) on [B={B},1,F={F},T={T}]", "l2": "flushed between timed iterations"},
             "e2e": {"value": ms_e2e / args.steps, "unit": wl["unit"], "h2d_bytes_per_step": B * F * T * 4 + 8 * B, "d2h_bytes_per_step": B * T * 4},
             "gpu_launches": launches, "clocks": clk.summary(),
-            "roofline": {"kernel": "fs2k_mas_fwd", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"]}}
+            "roofline": {"kernel": "fs2k_mas_fwd", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": ncu_traffic(wl_name, "fs2k_mas_fwd"), "peak_source": pk["source"]}}
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import intops
 
