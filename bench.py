@@ -832,7 +832,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--also", default="train_c2@bf16,synth_c1,synth_c1@bf16,synth_c4@bf16,synth_c5@bf16,mas_c2,mas_c5", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
+    ap.add_argument("--also", default="train_c2@bf16,train_stream@bf16,synth_c1,synth_c1@bf16,synth_c4@bf16,synth_c5@bf16,mas_c2,mas_c5", help="extra workloads measured briefly and attached under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python-driven launch per kernel")
     ap.add_argument("--precision", default=None, choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3"],
@@ -881,6 +881,10 @@ def main():
             else:
                 _ops.set_precision(prec or args.precision, args.backward_precision)
             try:
+                if name == "train_stream":  # shape-diverse stream: exact shapes vs opt-in bucketed padding (run_train_stream)
+                    line["also"][entry] = run_train_stream(a2, WORKLOADS["train_c2"], device)
+                    line["also"][entry]["dtype"] = DTYPES[_ops.PRECISION]
+                    continue
                 sub = run_ours(a2, name, WORKLOADS[name], rank, world, device)
                 if prec:
                     sub["dtype"] = f"{sub.get('dtype')} / decoder+postnet {prec[4:]} (reduced-precision mode, mel L1 <= 1e-2)" if prec.startswith("dec-") else sub.get("dtype")

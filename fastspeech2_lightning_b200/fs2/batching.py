@@ -39,8 +39,19 @@ def _as_numpy(x):
     return x
 
 
-def collate_to_device(data, device, learn_alignment: bool = True) -> dict:
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m if m and m > 1 else n
+
+
+def collate_to_device(data, device, learn_alignment: bool = True, pad_multiple=None) -> dict:
     """`collate_method(data, learn_alignment)` with the result on `device` (see the module docstring).
+
+    `pad_multiple=(text_multiple, mel_multiple)` (opt-in, not reference behaviour): pad to the next multiple instead of to
+    the batch maximum (dataset.py:257-293), so that a stream of batches falls into a few (T, F) shapes and
+    `FastSpeech2.optimization_step` replays captured graphs instead of running every new shape eagerly.  Padding is live
+    in this model (BatchNorm batch statistics, convolution edges and the full-rectangle loss means see it), so results
+    differ from the exact-shape batch exactly as they would if the batch contained one longer utterance; lengths, masks
+    and every valid position of the inputs are unchanged.
 
     Tensor / ndarray valued keys are padded on the device; int keys become int32 tensors; everything else (strings,
     None, floats) stays a Python list, as in the reference.  `max_src_len` / `max_mel_len` are 0-d int32 host tensors
@@ -54,6 +65,11 @@ def collate_to_device(data, device, learn_alignment: bool = True) -> dict:
     has_mel = cols.get("mel", [None])[0] is not None
     mel_lens = np.array([int(m.shape[0]) for m in cols["mel"]], dtype=np.int32) if has_mel else None
     max_mel = int(mel_lens.max()) if has_mel else 1_000_000
+    exact_text, exact_mel = max_text, max_mel
+    if pad_multiple is not None:
+        max_text = _round_up(max_text, int(pad_multiple[0]))
+        if has_mel:
+            max_mel = _round_up(max_mel, int(pad_multiple[1]))
 
     # ---- plan: every array-valued key becomes (items as contiguous 4-byte-word arrays, rows, cols, out shape / dtype)
     plans, small = [], {}
@@ -78,6 +94,8 @@ def collate_to_device(data, device, learn_alignment: bool = True) -> dict:
                 rows = [x.shape[0] for x in items]
                 cws = [trailing * wpe] * B
                 rmax = max(rows)
+                if pad_multiple is not None:  # frame-level keys follow the padded mel length, token-level keys the padded text length
+                    rmax = max_mel if (has_mel and rmax == exact_mel) else (max_text if rmax == exact_text else rmax)
                 out_shape, cmax = (B, rmax) + tuple(items[0].shape[1:]), trailing * wpe
             offs = []
             for x in items:
@@ -129,6 +147,38 @@ def collate_to_device(data, device, learn_alignment: bool = True) -> dict:
         out["mel_lens"] = None
     out["max_mel_len"] = torch.tensor(max_mel, dtype=torch.int32) if has_mel else max_mel
     out["_staging"] = dev_stage  # keeps the small views' storage alive with the batch
+    return out
+
+
+def pad_batch_to_multiple(batch: dict, pad_multiple) -> dict:
+    """The opt-in bucketed padding of `collate_to_device(pad_multiple=...)` for an already collated batch dict: every tensor
+    dimension that is the batch's `max_src_len` (`max_mel_len`) is zero-padded to the next multiple of `pad_multiple[0]`
+    (`[1]`), and the two maxima are updated.  Lengths and valid values are untouched.  Not reference behaviour — see
+    `collate_to_device`."""
+    T, F = int(batch["max_src_len"]), int(batch["max_mel_len"])
+    has_mel = batch.get("mel_lens") is not None and F < 1_000_000
+    T2 = _round_up(T, int(pad_multiple[0]))
+    F2 = _round_up(F, int(pad_multiple[1])) if has_mel else F
+    if (T2, F2) == (T, F):
+        return batch
+    if has_mel and T == F:
+        raise ValueError("pad_batch_to_multiple cannot tell token-level from frame-level keys when max_src_len == max_mel_len")
+    out = dict(batch)
+    for k, v in batch.items():
+        if not torch.is_tensor(v) or v.dim() < 2:
+            continue
+        # dimension 1 is the ragged one (pad_sequence); only the attention prior `duration` [B,F,T] is ragged in two
+        pads = []
+        for d in range(v.dim() - 1, 0, -1):  # F.pad takes the last dimension first
+            n = v.shape[d]
+            ragged = d == 1 or (k == "duration" and v.dim() == 3)
+            target = n if not ragged else (F2 if (has_mel and n == F) else (T2 if n == T else n))
+            pads += [0, target - n]
+        if any(pads):
+            out[k] = torch.nn.functional.pad(v, pads)
+    out["max_src_len"] = torch.tensor(T2, dtype=torch.int32)
+    if has_mel:
+        out["max_mel_len"] = torch.tensor(F2, dtype=torch.int32)
     return out
 
 

@@ -289,7 +289,8 @@ class FastSpeech2(_Base):
         if runner is None or runner.opt is not self.optimizer:
             from ..graphs import GraphedTrainStep
 
-            runner = self._train_runner = GraphedTrainStep(self, self.optimizer, self.scheduler)
+            # `train_graph_cache`: how many captured batch shapes are kept (LRU); raise it for shape-diverse streams
+            runner = self._train_runner = GraphedTrainStep(self, self.optimizer, self.scheduler, max_graphs=int(getattr(self, "train_graph_cache", 16)))
         if use_cuda_graph:
             return runner(batch)
         dev = self.optimizer.flat_p.device

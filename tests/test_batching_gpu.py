@@ -62,3 +62,31 @@ def test_trim_predictions_equals_per_item_slicing():
     for b in range(B):
         ref = mel[b][: int(lens[b])].cpu().transpose(0, 1)
         assert out[b].shape == ref.shape and torch.equal(out[b], ref), b
+
+
+def test_bucketed_padding_keeps_lengths_and_valid_values_and_the_step_runs():
+    """Opt-in `pad_multiple` padding (fs2.batching): shapes are rounded up, lengths / valid values unchanged, padding is zero,
+    and the training step accepts the batch; `collate_to_device(pad_multiple=...)` pads to the same shapes."""
+    from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.fs2.batching import collate_to_device, pad_batch_to_multiple
+
+    b = synthetic.make_batch(3, (20, 27), seed=12, learn_alignment=True)
+    T, F = int(b["max_src_len"]), int(b["max_mel_len"])
+    p = pad_batch_to_multiple(b, (8, 32))
+    T2, F2 = int(p["max_src_len"]), int(p["max_mel_len"])
+    assert (T2, F2) == ((T + 7) // 8 * 8, (F + 31) // 32 * 32) and (T2, F2) != (T, F)
+    assert p["mel"].shape == (3, F2, 80) and p["duration"].shape == (3, F2, T2) and p["text"].shape == (3, T2) and p["pitch"].shape == (3, F2)
+    assert torch.equal(p["mel"][:, :F], b["mel"]) and float(p["mel"][:, F:].abs().sum()) == 0.0
+    assert torch.equal(p["duration"][:, :F, :T], b["duration"]) and torch.equal(p["src_lens"], b["src_lens"]) and torch.equal(p["mel_lens"], b["mel_lens"])
+    assert pad_batch_to_multiple(p, (8, 32)) is p       # already on the grid
+    items = _items(3, True, with_mel=True, seed=3)
+    exact = collate_to_device(items, DEV, True)
+    padded = collate_to_device(items, DEV, True, pad_multiple=(8, 32))
+    Te, Fe = int(exact["max_src_len"]), int(exact["max_mel_len"])
+    assert int(padded["max_src_len"]) == (Te + 7) // 8 * 8 and int(padded["max_mel_len"]) == (Fe + 31) // 32 * 32
+    for k, v in exact.items():
+        if torch.is_tensor(v) and v.dim() >= 2:
+            w = padded[k]
+            sl = tuple(slice(0, n) for n in v.shape)
+            assert torch.equal(w[sl], v), k
+            assert float(w.float().abs().sum()) == float(v.float().abs().sum()), k   # everything outside is zero
