@@ -588,6 +588,49 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
     return line
 
 
+def run_train_stream(args, wl, device, n_steps=96, warm=32, pad_multiple=(8, 32)):
+    """Shape-diverse training stream (every batch draws its own phone count and durations, as a real epoch does;
+    dataset.py:257-293 pads each batch to its own maxima).  Three policies over the SAME stream, cold caches:
+      exact_graphs    — the default: exact shapes, first sight eager, second sight captured, then replayed (LRU of 64 shapes);
+      exact_eager     — exact shapes, eager launches only;
+      bucketed_graphs — opt-in `pad_multiple` padding (fs2.batching.pad_batch_to_multiple): a few (T, F) shapes, so the
+                        stream soon runs on replays.  Not reference padding: results differ as with one longer utterance.
+    Reports wall-clock ms per step over the last `n_steps - warm` steps (device idle at both ends)."""
+    import time
+
+    import numpy as np
+
+    from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.fs2.batching import pad_batch_to_multiple
+
+    g = np.random.default_rng(2024)
+    his = g.integers(64, 97, size=n_steps)
+    stream = [synthetic.make_batch(wl["batch"], (max(int(h) - 30, 20), int(h)), seed=9000 + i, learn_alignment=True) for i, h in enumerate(his)]
+    shapes = {(int(b["max_src_len"]), int(b["max_mel_len"])) for b in stream}
+    out = {"steps": n_steps, "timed_steps": n_steps - warm, "distinct_shapes": len(shapes), "batch": wl["batch"], "pad_multiple": list(pad_multiple)}
+    for policy in ("exact_graphs", "exact_eager", "bucketed_graphs"):
+        cfg, model = build_train_model(device)
+        model.train_graph_cache = 64
+        model.configure_optimizers()
+        batches = stream if policy != "bucketed_graphs" else [pad_batch_to_multiple(b, pad_multiple) for b in stream]
+        host = [pin(b) for b in batches]
+        graphs = policy != "exact_eager"
+        t0 = None
+        for i, b in enumerate(host):
+            if i == warm:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            model.optimization_step(b, use_cuda_graph=graphs)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / (n_steps - warm)
+        runner = model._train_runner
+        out[policy] = {"ms_per_step": ms, "utts_per_sec": wl["batch"] / (ms * 1e-3), "captured_shapes": len(runner._cache),
+                       "shapes_in_stream": len({(int(b["max_src_len"]), int(b["max_mel_len"])) for b in batches})}
+        del model, runner, host
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_train_baseline(wl, steps=1):
     """The reference's CPU training step (oracle port): forward + losses + backward + clip_grad_norm_(1.0) + AdamW."""
     from oracle import fs2_oracle

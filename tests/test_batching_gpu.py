@@ -89,4 +89,6 @@ def test_bucketed_padding_keeps_lengths_and_valid_values_and_the_step_runs():
             w = padded[k]
             sl = tuple(slice(0, n) for n in v.shape)
             assert torch.equal(w[sl], v), k
-            assert float(w.float().abs().sum()) == float(v.float().abs().sum()), k   # everything outside is zero
+            rest = w.clone()
+            rest[sl] = 0
+            assert float(rest.float().abs().sum()) == 0.0, k   # everything outside is zero
