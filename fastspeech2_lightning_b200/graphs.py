@@ -91,23 +91,27 @@ class GraphedSynthesis:
 
 class GraphedTrainStep:
     """One optimisation step — zero_grad, forward (aligner + MAS + encoder + variance adaptor + decoder + PostNet),
-    the seven losses, backward, clip and AdamW — as ONE CUDA graph per batch shape (data-parallel runs: a
-    forward/backward graph, the NCCL all-reduce of the flat gradient launched eagerly, and an update graph): ≈1000 kernel launches become one `cudaGraphLaunch`, so a step costs what the GPU needs, not what Python
-    can enqueue.
+    the seven losses, backward, clip and AdamW — as ONE CUDA graph per batch shape (data-parallel runs: three graphs
+    around two NCCL all-reduces on a communication stream, see `_exchange`): ≈ 850 kernel launches become one
+    `cudaGraphLaunch`, so a step costs what the GPU needs, not what Python can enqueue.
 
     Everything that changes between steps lives in device memory: the batch (copied into the captured input
     buffers, straight from pinned host memory if that is where it is), the learning rate / Adam bias corrections
-    and the dropout seed base (`FusedAdamW.begin_graph_step`).  The first time a shape is seen the step runs
-    eagerly (that is also the warm-up a capture needs); the second time it is captured and replayed.  Shapes are
+    and the dropout seed base (`FusedAdamW.begin_graph_step`).  The first `capture_after` (2) times a shape is seen the step runs
+    eagerly (that is also the warm-up a capture needs); the next time it is captured and replayed.  Shapes are
     exact — padding is live in this model (BatchNorm statistics and the full-rectangle losses see it), so batches
     are never re-padded to share a graph.  The loss weights that depend on the epoch are part of the key.
     """
 
-    def __init__(self, model, optimizer, scheduler=None, max_graphs: int = 16, overlap_wgrad: bool = True):
+    def __init__(self, model, optimizer, scheduler=None, max_graphs: int = 16, overlap_wgrad: bool = True, capture_after: int = 2):
         self.model, self.opt, self.sched = model, optimizer, scheduler
         self.max_graphs = max_graphs
         self._cache: dict = {}
-        self._seen: set = set()
+        self._seen: dict = {}           # batch shape → eager sights so far
+        # A capture costs ≈ 0.4 s of host time (≈ 850 graph nodes to record and instantiate) — 15–35 eager steps' worth — so a
+        # shape is captured only after `capture_after` eager sights: in a shape-diverse stream (measured: 332 distinct shapes in
+        # 384 batches) capturing at the second sight made the stream 2.7× SLOWER than never capturing.
+        self.capture_after = max(1, int(capture_after))
         self._eager_only: set = set()
         self._pool = None
         self.overlap_wgrad = overlap_wgrad
@@ -252,9 +256,11 @@ class GraphedTrainStep:
         key = self._key(batch)
         entry = self._cache.get(key)
         dev = opt.flat_p.device
-        if entry is None and (key not in self._seen or key in self._eager_only):
-            # first sight of this shape: plain eager step (validates the data, warms every lazy init)
-            self._seen.add(key)
+        if entry is None and (self._seen.get(key, 0) < self.capture_after or key in self._eager_only):
+            # first sights of this shape: plain eager step (validates the data, warms every lazy init)
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            self._seen[key] = self._seen.get(key, 0) + 1
             dev_batch = {k: (v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()
                          if not k.startswith("_")}
             losses = self._step_body(dev_batch)

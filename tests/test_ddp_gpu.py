@@ -66,7 +66,7 @@ def _worker(rank, world, port, precision, ref_path, out_path):
 
     batch = synthetic.batch_to(halves[rank], dev)
     losses = []
-    for _ in range(3):               # eager first sight, capture, replay
+    for _ in range(4):               # two eager sights, capture + replay, replay
         losses.append(float(model.optimization_step(batch)["total"]))
     flat = model.optimizer.flat_p.detach().cpu()
     if rank == 0:
@@ -92,7 +92,7 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(precision,
         model.configure_optimizers()
         full = synthetic.batch_to(_cat(halves), dev)
         assert int(halves[0]["max_mel_len"]) == int(halves[1]["max_mel_len"]) == 80
-        ref_losses = [float(model.optimization_step(full)["total"]) for _ in range(3)]
+        ref_losses = [float(model.optimization_step(full)["total"]) for _ in range(4)]
         with tempfile.TemporaryDirectory() as td:
             ref_path, out_path = os.path.join(td, "ref.pt"), os.path.join(td, "out.pt")
             torch.save({"flat": model.optimizer.flat_p.detach().cpu(), "losses": ref_losses}, ref_path)
@@ -103,7 +103,7 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(precision,
             res = torch.load(out_path)
     finally:
         ops.set_precision("tf32x3")
-    print(f"{precision}: 2-rank vs 1-rank parameters after 3 steps: max err / max|p| = {res['err']:.2e}; "
+    print(f"{precision}: 2-rank vs 1-rank parameters after 4 steps: max err / max|p| = {res['err']:.2e}; "
           f"rank-0 losses {res['losses']} vs full-batch {res['ref_losses']}")
     assert res["err"] <= tol, res
 
