@@ -588,7 +588,7 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
     return line
 
 
-def run_train_stream(args, wl, device, n_steps=384, warm=256, pad_multiple=(8, 32)):
+def run_train_stream(args, wl, device, n_steps=768, warm=512, pad_multiple=(8, 32)):
     """Shape-diverse training stream (every batch draws its own phone count and durations, as a real epoch does;
     dataset.py:257-293 pads each batch to its own maxima).  Three policies over the SAME stream, cold caches:
       exact_graphs    — the default: exact shapes, first sight eager, second sight captured, then replayed (LRU of 64 shapes);

@@ -8,24 +8,31 @@ i.e. given durations (teacher-forced synthesis) with `validate_durations = False
 """
 from __future__ import annotations
 
+import gc
+import itertools
 import weakref
 
 import torch
 
 from ._lib import check, lib
 
-_ARMED_SEED_BASE = 0  # device address the library's dropout seed-base pointer currently holds (0 = none)
+_ARMED_SEED_BASE = 0   # device address the library's dropout seed-base pointer currently holds (0 = none)
+_ARMED_OWNER = 0       # token of the runner that armed it (the allocator may hand a dead counter's address to a new optimizer)
+_owner_tokens = itertools.count(1)
 
 
-def _clear_seed_base(ptr: int) -> None:
-    """The counter's owner is gone: a dangling pointer would make every later dropout kernel read freed memory."""
-    global _ARMED_SEED_BASE
-    if _ARMED_SEED_BASE == ptr:
+def _clear_seed_base(ptr: int, owner: int) -> None:
+    """The counter's owner is gone: a dangling pointer would make every later dropout kernel read freed memory.  Only the
+    runner that armed the pointer clears it, and never while a capture is in progress (the reset is a synchronous copy to a
+    device symbol — it would invalidate the capture; the next step re-arms anyway)."""
+    global _ARMED_SEED_BASE, _ARMED_OWNER
+    if _ARMED_SEED_BASE == ptr and _ARMED_OWNER == owner:
         try:
-            lib().fs2k_set_dropout_seed_base(None)
+            if not torch.cuda.is_current_stream_capturing():
+                lib().fs2k_set_dropout_seed_base(None)
         except Exception:
             pass
-        _ARMED_SEED_BASE = 0
+        _ARMED_SEED_BASE = _ARMED_OWNER = 0
 
 
 def _signature(batch) -> tuple:
@@ -64,8 +71,15 @@ class GraphedSynthesis:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph), torch.no_grad():
-            static_out = model(static_in, inference=True)
+        gc_was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()  # destructors of collected CUDA objects must not run inside the capture (see GraphedTrainStep)
+        try:
+            with torch.cuda.graph(graph), torch.no_grad():
+                static_out = model(static_in, inference=True)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
         return graph, static_in, static_out
 
     def __call__(self, batch, non_blocking: bool = True):
@@ -123,17 +137,18 @@ class GraphedTrainStep:
         # every dropout kernel adds *seed_base to its by-value seed (fresh masks on graph replays).  The pointer is
         # process-wide inside the library: it is re-armed before every step of THIS runner (another runner may have
         # pointed it at its own counter) and cleared when the optimizer — the owner of the counter — goes away.
+        self._token = next(_owner_tokens)
         self._arm_seed_base()
-        weakref.finalize(optimizer, _clear_seed_base, optimizer.seed_base.data_ptr())
+        weakref.finalize(optimizer, _clear_seed_base, optimizer.seed_base.data_ptr(), self._token)
 
     def _arm_seed_base(self) -> None:
-        global _ARMED_SEED_BASE
+        global _ARMED_SEED_BASE, _ARMED_OWNER
         ptr = self.opt.seed_base.data_ptr()
-        if _ARMED_SEED_BASE != ptr:
+        if _ARMED_SEED_BASE != ptr or _ARMED_OWNER != self._token:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("the dropout seed base must be armed before the capture starts")
             check(lib().fs2k_set_dropout_seed_base(ptr), "fs2k_set_dropout_seed_base")
-            _ARMED_SEED_BASE = ptr
+            _ARMED_SEED_BASE, _ARMED_OWNER = ptr, self._token
 
     def _early_params(self):
         """Data-parallel runs: the parameters behind the decoder's input (decoder, mel_linear, PostNet).  Their gradients are
@@ -276,6 +291,12 @@ class GraphedTrainStep:
             prev_validate, va.validate_durations = va.validate_durations, False  # the eager first sight validated
             opt.device_state = True
             torch.cuda.synchronize()
+            # No cyclic garbage collection inside the capture: collecting an old model / runner there runs CUDA calls from its
+            # destructors and finalizers (graph and pool destruction, the seed-base reset), which invalidates a capture in
+            # progress ("operation failed due to a previous error during capture", seen intermittently between tests).
+            gc_was_enabled = gc.isenabled()
+            gc.collect()
+            gc.disable()
             # data-parallel: the NCCL all-reduces stay OUTSIDE the graphs.  forward + backward down to the decoder's input
             # → [all-reduce of the decoder / PostNet gradients ‖ rest of the backward] → all-reduce of the rest → update;
             # single GPU: one graph for everything
@@ -307,6 +328,8 @@ class GraphedTrainStep:
                 torch.cuda.synchronize()
                 return self(batch, non_blocking)
             finally:
+                if gc_was_enabled:
+                    gc.enable()
                 opt.device_state = False
                 va.validate_durations = prev_validate
             if self._pool is None:

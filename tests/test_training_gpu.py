@@ -135,10 +135,11 @@ def test_graph_replay_draws_fresh_dropout_masks_and_learning_rates():
         g["weight_decay"] = 0.0
     model.scheduler.base_lrs = [0.0 for _ in model.scheduler.base_lrs]  # frozen parameters: only dropout varies
     seen = []
-    for i in range(4):
+    for i in range(6):  # two eager sights, capture + replay, three more replays
         losses = model.optimization_step(batch)
         seen.append({k: float(v) for k, v in losses.items()})
-    replays = seen[1:]
+    assert len(model._train_runner._cache) == 1
+    replays = seen[2:]
     assert len({round(r["postnet"], 9) for r in replays}) == len(replays), replays  # fresh PostNet dropout masks
     assert all(abs(r["spec"] - replays[0]["spec"]) < 1e-6 for r in replays)          # no dropout before the PostNet
     # now let the schedule drive the captured optimizer: parameters must move by the current lr, not the captured one
@@ -243,7 +244,7 @@ def test_repacked_conv_weights_follow_the_optimizer(graph):
     w = next(p for n, p in model.named_parameters() if n.startswith("postnet") and p.dim() == 3 and p.shape[-1] > 1)
     before = w.detach().clone()
     first = ops.conv_weight_taps(w).clone()
-    steps = 4 if graph else 2
+    steps = 5 if graph else 2
     for _ in range(steps):
         model.optimization_step(batch, use_cuda_graph=graph)
     assert float((w.detach() - before).abs().max()) > 1e-5  # the optimizer moved it
