@@ -46,10 +46,10 @@ lr_scan_kernel(const int* __restrict__ dur, int B, int T, int* __restrict__ cum,
     if (lane == 0) total[b] = carry;
 }
 
-constexpr int kLrTile = 64;      // frames per CTA
+constexpr int kLrTile = 16;  // frames per CTA: 2 rows per warp (64 left one CTA per SM at B = 16, F = 500 — a serial chain of 8 dependent row copies per warp)
 constexpr int kLrMaxSmemT = 2048;
 
-// ---- gather: CTA = 64 consecutive frames of one utterance ----
+// ---- gather: CTA = kLrTile consecutive frames of one utterance ----
 template <bool POS>
 __global__ void __launch_bounds__(256)
 lr_gather_kernel(const float* __restrict__ x,    // [B,T,D]
