@@ -13,7 +13,7 @@
 
 namespace fs2k {
 
-constexpr int kDwTile = 32;   // frames per CTA
+constexpr int kDwTile = 16;   // frames per CTA
 constexpr int kDwUnroll = 8;  // frames whose inputs are in flight together
 
 template <int K, bool GLU, int MODE>
