@@ -404,3 +404,45 @@ def test_cut_backward_with_overlapped_exchange_equals_the_single_graph_step(prec
         assert err < (5e-4 if precision == "tf32x3" else 2e-3), err
     finally:
         ops.set_precision("tf32x3")
+
+
+def test_batches_from_the_device_collate_replay_the_captured_step():
+    """`fs2.batching.collate_to_device` output fed to `optimization_step`: the private `_staging` blob (whose size depends on
+    the valid lengths) is not part of the graph key, so batches with the same padded shape but different lengths hit the same
+    captured graph (two eager sights, one capture, then replays), and `_seen` does not grow."""
+    from fastspeech2_lightning_b200 import synthetic
+    from fastspeech2_lightning_b200.fs2.batching import collate_to_device
+    from fastspeech2_lightning_b200.fs2.config import FastSpeech2Config
+    from fastspeech2_lightning_b200.fs2.model import FastSpeech2
+
+    def items(seed):
+        g = np.random.default_rng(seed)
+        out = []
+        for b in range(4):
+            T = 20 if b == 0 else int(g.integers(8, 20))          # item 0 fixes the padded shape (T = 20, F = 60)
+            dur = np.full(T, 3) if b == 0 else g.integers(1, 4, size=T)
+            F = int(dur.sum())
+            out.append({"text": torch.from_numpy(g.integers(1, 27, size=T).astype(np.int64)),
+                        "mel": torch.from_numpy(g.standard_normal((F, 80)).astype(np.float32)),
+                        "duration": torch.from_numpy(g.random((F, T)).astype(np.float32)),
+                        "pitch": torch.from_numpy(g.standard_normal(F).astype(np.float32)),
+                        "energy": torch.from_numpy(g.standard_normal(F).astype(np.float32)),
+                        "speaker_id": 0, "language_id": 0, "basename": f"u{seed}-{b}", "duration_control": 1.0,
+                        "mel_style_reference": None})
+        return out
+
+    model = FastSpeech2(FastSpeech2Config(), stats=synthetic.DEFAULT_STATS)
+    synthetic.fill_weights_(model, seed=21)
+    model.train()
+    model = model.to(DEV)
+    model.fused_grad_clip = 1.0
+    model.configure_optimizers()
+    sizes = set()
+    for i in range(5):
+        batch = collate_to_device(items(100 + i), DEV, True)
+        sizes.add(batch["_staging"].numel())
+        loss = float(model.optimization_step(batch)["total"])
+        assert loss == loss
+    runner = model._train_runner
+    assert len(sizes) > 1                                   # the staging blobs did differ …
+    assert len(runner._cache) == 1 and len(runner._seen) == 1 and runner._n_replays >= 2   # … and the shape was captured once and replayed
