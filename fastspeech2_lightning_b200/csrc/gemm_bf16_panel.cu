@@ -210,24 +210,34 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
             // and trip 0's are issued before the wait for the accumulator
             float4 res_n[4];
             float rm_n[4];
-            uint2 pre_n[4];  // DACT: the saved bf16 pre-activations of the trip (read inline they exposed one global-load latency
-                             // per trip: 119 µs per decoder FFN dgrad against 55 µs for the forward of the same shape)
+            // DACT: the saved bf16 pre-activations of ALL 32 rows of this lane's columns are requested before the wait for the
+            // accumulator (16 loads in flight behind the MMAs of the block).  Read inline they exposed one global-load latency per
+            // trip (119 µs per decoder FFN dgrad against 55 µs for the forward of the same shape); one trip ahead still 104 µs.
             constexpr bool PIPE_PRE = EPI == PB_EPI_DACT;
+            uint2 pre_all[PIPE_PRE ? 16 : 1];
+            if (PIPE_PRE) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = t * 8 + u * 2 + rsub;
+                        pre_all[t * 4 + u] = r < rows_left ? *reinterpret_cast<const uint2*>(p_pre + (size_t)(mrow0 + t * 8 + u * 2) * ldp + ncol)
+                                                           : make_uint2(0u, 0u);
+                    }
+            }
             auto load_trip = [&](int rb) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int r = rb + u * 2 + rsub;
                     res_n[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     rm_n[u] = 1.f;
-                    pre_n[u] = make_uint2(0u, 0u);
                     if (r < rows_left) {
                         if (p_res) res_n[u] = *reinterpret_cast<const float4*>(p_res + (size_t)(mrow0 + rb + u * 2) * ldr + ncol);
                         if (p_mask) rm_n[u] = p_mask[mrow0 + rb + u * 2] ? 1.f : 0.f;
-                        if (PIPE_PRE) pre_n[u] = *reinterpret_cast<const uint2*>(p_pre + (size_t)(mrow0 + rb + u * 2) * ldp + ncol);
                     }
                 }
             };
-            if (p_res || p_mask || PIPE_PRE) load_trip(0);
+            if (p_res || p_mask) load_trip(0);
             mbar_wait(smem_u32(&s_tmem_full[buf]), (jj >> 1) & 1);
             tc_fence_after();
             {
@@ -255,9 +265,13 @@ gemm_bf16_panel_kernel(const __grid_constant__ CUtensorMap tmB, const float* __r
                 for (int u = 0; u < 4; ++u) {
                     res[u] = (p_res || p_mask) ? res_n[u] : make_float4(0.f, 0.f, 0.f, 0.f);
                     rm[u] = (p_res || p_mask) ? rm_n[u] : 1.f;
-                    pre[u] = pre_n[u];
+                    pre[u] = PIPE_PRE ? pre_all[u] : make_uint2(0u, 0u);
                 }
-                if ((p_res || p_mask || PIPE_PRE) && rb + 8 < 32) load_trip(rb + 8);
+                if (PIPE_PRE) {  // next trip's values move to the front (the trip loop is not unrolled: static register indices)
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) pre_all[i] = pre_all[i + 4];
+                }
+                if ((p_res || p_mask) && rb + 8 < 32) load_trip(rb + 8);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int r = rb + u * 2 + rsub;
