@@ -588,7 +588,7 @@ def run_train(args, wl_name, wl, rank, world, device, pk):
     return line
 
 
-def run_train_stream(args, wl, device, n_steps=768, warm=512, pad_multiple=(8, 32)):
+def run_train_stream(args, wl, device, n_steps=768, warm=512, pad_multiple=(8, 32), policies=("exact_graphs", "exact_eager", "bucketed_graphs")):
     """Shape-diverse training stream (every batch draws its own phone count and durations, as a real epoch does;
     dataset.py:257-293 pads each batch to its own maxima).  Three policies over the SAME stream, cold caches:
       exact_graphs    — the default: exact shapes, first sight eager, second sight captured, then replayed (LRU of 64 shapes);
@@ -609,7 +609,7 @@ def run_train_stream(args, wl, device, n_steps=768, warm=512, pad_multiple=(8, 3
     stream = [synthetic.make_batch(wl["batch"], (max(int(h) - 30, 20), int(h)), seed=9000 + i, learn_alignment=True) for i, h in enumerate(his)]
     shapes = {(int(b["max_src_len"]), int(b["max_mel_len"])) for b in stream}
     out = {"steps": n_steps, "timed_steps": n_steps - warm, "distinct_shapes": len(shapes), "batch": wl["batch"], "pad_multiple": list(pad_multiple)}
-    for policy in ("exact_graphs", "exact_eager", "bucketed_graphs"):
+    for policy in policies:
         cfg, model = build_train_model(device)
         model.train_graph_cache = 64
         model.configure_optimizers()

@@ -127,8 +127,8 @@ class GraphedTrainStep:
         # 384 batches) capturing at the second sight made the stream 2.7× SLOWER than never capturing.
         self.capture_after = max(1, int(capture_after))
         # … and capturing backs off altogether when captured shapes are not coming back: a capture (with the allocator flush
-        # torch.cuda.graph does around it) costs ≈ 1 s end to end, so after the first 8 captures a new shape is only captured
-        # while the stream has shown at least 16 replays per capture (measured on 604 distinct shapes in 768 batches:
+        # torch.cuda.graph does around it) costs ≈ 1 s end to end, so after the first 4 captures a new shape is only captured
+        # while the stream has shown at least 4 replays per capture (measured on 604 distinct shapes in 768 batches:
         # 90 ms per step with unconditional capturing against 24 ms eager).
         self._n_captures = 0
         self._n_replays = 0
@@ -266,7 +266,7 @@ class GraphedTrainStep:
         return losses
 
     def _capture_pays(self) -> bool:
-        return self._n_captures < 8 or self._n_replays >= 16 * self._n_captures
+        return self._n_captures < 4 or self._n_replays >= 4 * self._n_captures
 
     def _key(self, batch):
         t = self.model.config.training
