@@ -172,11 +172,13 @@ int fs2k_attention_bf16(const void* qkv_bf16, const int* lens, int B, int L, int
 int fs2k_attention_bwd_bf16(const void* qkv_bf16, const float* out, const float* lse, const float* dout,
                             const void* dout_bf16, const int* lens, int B, int L, int H, int head_dim, float dropout_p,
                             long seed, float* delta, float* dqkv, const int* order, fs2k_stream_t stream);
-/* same with either operand already bf16 in HBM (read by TMA instead of the converting producer warps); ld % 8 == 0 for those */
 /* Split-K reduction of the single-tap weight gradients (both wgrad entry points).  1 (default): partial tiles are added into
    dW by 16-byte reductions resolved in L2 — no workspace traffic, no reduce launch, summation order not fixed; 0: workspace +
    deterministic reduce kernel.  Multi-tap (conv) gradients always use the workspace. */
 int fs2k_wgrad_set_atomic(int enabled);
+/* fs2k_gemm_wgrad_bf16 (below) with either operand already bf16 in HBM (read by TMA instead of the converting producer warps);
+   ld % 8 == 0 for those.  Replaces the weight-gradient half of autograd through nn.Linear / nn.Conv1d in the Conformer stacks
+   and the PostNet (torchaudio conformer.py:103-108,151-153; fs2/layers.py:143-212) in the bf16 mode. */
 int fs2k_gemm_wgrad_bf16_ex(const void* G, int g_is_bf16, int ldg, const void* X, int x_is_bf16, int ldx, int B, int L,
                             int N, int K, int taps, int pad, void* workspace, size_t workspace_bytes,
                             float* dW_param_layout, int accumulate, fs2k_stream_t stream);
